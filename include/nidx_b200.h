@@ -1,0 +1,176 @@
+/* nidx_b200 — C ABI of the B200-native nidx search hot path (libnidx_b200.so).
+ *
+ * This is the drop-in boundary: every entry point replaces one Rust interface of the reference
+ * (cited per function) and is what a cgo/FFI/ctypes binding on the reference side binds
+ * (INTEGRATION.md shows the Rust `extern "C"` block).  Plain pointers and sizes only; the caller
+ * owns every buffer it passes, the library owns the handles and all device memory.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative NIDX_E* code on failure;
+ *     nidx_last_error() returns the message of the calling thread's last failure
+ *     (reference: anyhow::Error / VectorErr strings, nidx_vector/src/lib.rs:203-232).
+ *   - `mem` arguments say where the caller's buffers live: NIDX_MEM_HOST (the library copies
+ *     host<->device inside the call) or NIDX_MEM_DEVICE (pointers are device pointers on the
+ *     index's GPU; nothing is copied).  `stream` is a cudaStream_t (NULL = default stream); calls
+ *     with NIDX_MEM_DEVICE are asynchronous on it, calls with NIDX_MEM_HOST return after the
+ *     results are in the host buffers.
+ *   - search entry points are re-entrant: they may be called concurrently from many threads on
+ *     one handle (reference: searchers are Sync+Send behind an Arc, index_cache.rs:41-47).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with NIDX_ENODEVICE.
+ */
+#ifndef NIDX_B200_H
+#define NIDX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIDX_OK 0
+#define NIDX_EINVAL (-1)     /* bad argument (VectorErr::InconsistentDimensions, ...) */
+#define NIDX_ENODEVICE (-2)  /* no usable CUDA device */
+#define NIDX_ECUDA (-3)      /* CUDA runtime error */
+#define NIDX_EIO (-4)        /* segment file error */
+#define NIDX_ESTATE (-5)     /* e.g. HNSW search on an index without a graph */
+#define NIDX_EOVERFLOW (-6)  /* an internal bounded structure overflowed; results incomplete */
+
+#define NIDX_MEM_HOST 0
+#define NIDX_MEM_DEVICE 1
+
+#define NIDX_SIM_DOT 0     /* config.rs:33-37 Similarity::Dot */
+#define NIDX_SIM_COSINE 1  /* Similarity::Cosine */
+
+#define NIDX_METHOD_AUTO 0   /* segment.rs:538 use_hnsw() cost model decides */
+#define NIDX_METHOD_HNSW 1   /* hnsw/search.rs:306-383 */
+#define NIDX_METHOD_BRUTE 2  /* segment.rs:569-623 */
+
+#define NIDX_NIL 0xFFFFFFFFu
+
+const char* nidx_last_error(void);
+/* Number of CUDA devices the library can use (0 => every other call fails). */
+int nidx_device_count(void);
+/* Kernel launches issued by this process through the library (bench.py's gpu_launches). */
+uint64_t nidx_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Vector segment  (reference: nidx_vector OpenSegment + VectorConfig, segment.rs / config.rs)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nidx_vec_segment nidx_vec_segment;
+
+typedef struct nidx_vec_config {
+    int32_t dimension;        /* VectorType::DenseF32{dimension}, config.rs:102-124 */
+    int32_t similarity;       /* NIDX_SIM_* */
+    int32_t multi_vector;     /* VectorCardinality::Multi: one result per paragraph */
+    int32_t m;                /* params.rs:40 M (also M_MAX);   0 => 30 */
+    int32_t m0;               /* params.rs:34 M_MAX_0;          0 => 60 */
+    int32_t ef_construction;  /* params.rs:43;                  0 => 100 */
+    int32_t ef_search;        /* params.rs:46;                  0 => 30 */
+    int32_t device;           /* CUDA device ordinal */
+} nidx_vec_config;
+
+/* segment::create's data-store half (segment.rs:199-239, data_store/v2.rs:54-80): take n vectors
+ * ([n][ld] f32, ld >= dimension) and, optionally, the paragraph address of every vector
+ * (vectors of one paragraph must be contiguous; NULL = one vector per paragraph).  Vectors are
+ * re-laid out in HBM as [n][ld4] rows (16-byte aligned) and their norms are precomputed.
+ * No graph yet: brute force works, HNSW needs nidx_vec_build_hnsw or nidx_vec_set_graph. */
+int nidx_vec_create(const nidx_vec_config* cfg, const float* vectors, uint64_t n, int32_t ld, int mem, const uint32_t* paragraph_of,
+                    nidx_vec_segment** out);
+
+/* Open a segment directory written by the reference (or by nidx_vec_save): vectors.bin
+ * (data_store/v2/vector_store.rs:33-68) + hnsw.graph (hnsw/disk/v2.rs:16-49) [+ hnsw.edges].
+ * Replaces segment::open (segment.rs:39-90) for the hot path's needs. */
+int nidx_vec_open(const nidx_vec_config* cfg, const char* dir, nidx_vec_segment** out);
+/* Write vectors.bin / hnsw.graph / hnsw.edges in the reference's formats (DiskHnswV2::serialize_to,
+ * hnsw/disk/v2.rs:213-218; VectorStoreWriter, vector_store.rs:113-146). */
+int nidx_vec_save(nidx_vec_segment* seg, const char* dir);
+void nidx_vec_close(nidx_vec_segment* seg);
+
+uint64_t nidx_vec_len(const nidx_vec_segment* seg);
+/* Device pointers of the resident data, for zero-copy consumers (bench, tests). */
+const float* nidx_vec_device_vectors(const nidx_vec_segment* seg, int32_t* ld_out);
+
+/* HnswBuilder (hnsw/build.rs:36-166) on the GPU: levels for all nodes first (initialize_graph),
+ * then batch-synchronous insertion (DESIGN.md "build"): batches of at most max_batch nodes search
+ * the frozen graph and are linked in ascending id.  seed: level RNG seed (reference uses 2). */
+int nidx_vec_build_hnsw(nidx_vec_segment* seg, uint64_t seed, int32_t max_batch, void* stream);
+
+/* Flat graph import / export (the layout in DESIGN.md; the oracle uses the same one).
+ * level[n] u8; adj0[n][s0] u32, adjU[rows][su] u32, NIDX_NIL padded; w0/wU edge similarities
+ * (may be NULL on import: search does not need them, merge/build does). Host pointers. */
+int nidx_vec_graph_dims(const nidx_vec_segment* seg, int32_t* s0, int32_t* su, uint64_t* upper_rows, uint32_t* entry_node,
+                        uint32_t* entry_layer);
+int nidx_vec_set_graph(nidx_vec_segment* seg, const uint8_t* level, const uint32_t* adj0, const float* w0, const uint32_t* adjU,
+                       const float* wU);
+int nidx_vec_get_graph(const nidx_vec_segment* seg, uint8_t* level, uint32_t* adj0, float* w0, uint32_t* adjU, float* wU);
+
+/* OpenSegment::apply_deletions (segment.rs:428-445): bit per paragraph, 1 = alive; NULL = all alive. */
+int nidx_vec_set_alive(nidx_vec_segment* seg, const uint64_t* alive_bits, int mem);
+
+typedef struct nidx_vec_search_params {
+    int32_t k;                /* VectorSearchRequest.result_per_page (request_types.rs:18-35) */
+    int32_t ef;               /* layer-0 width = max(k, ef) (hnsw/search.rs:338-345); 0 => config */
+    float min_score;          /* VectorSearchRequest.min_score */
+    int32_t with_duplicates;  /* VectorSearchRequest.with_duplicates */
+    int32_t method;           /* NIDX_METHOD_* */
+    const uint64_t* filter_bits; /* filter formula evaluated to a bitset over paragraphs
+                                    (segment.rs:516-534); NULL = no filter. Same `mem` as queries. */
+    uint64_t filter_matching; /* number of set bits in filter_bits ∧ alive (segment.rs:531), only read
+                                 by the NIDX_METHOD_AUTO cost model; 0 = unknown (count on device) */
+} nidx_vec_search_params;
+
+/* OpenSegment::search (segment.rs:477-567) for a batch of nq queries ([nq][ldq] f32).
+ * out_ids/out_scores are [nq][k] (vector address + similarity, descending; NIDX_NIL padded),
+ * out_counts[nq] the number of valid results per query. */
+int nidx_vec_search(nidx_vec_segment* seg, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p,
+                    uint32_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
+
+/* Searcher::_search's cross-segment / cross-shard top-k (searcher.rs:241-290 Fssc without the string
+ * keys, shard_merge.rs:332-348): merge n_parts partial results [n_parts][nq][k] (score desc) into
+ * [nq][k]; out_part[nq][k] receives the index of the part each winner came from.  Device pointers. */
+int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int32_t nq, int32_t k, uint32_t* out_ids,
+                    float* out_scores, int32_t* out_part, void* stream);
+
+/* Counters of the last HNSW search / build on this segment (for the roofline accounting,
+ * SURVEY 8d): [0] similarity evaluations, [1] node expansions, [2] visited-set overflows. */
+int nidx_vec_counters(nidx_vec_segment* seg, uint64_t out[3]);
+
+/* ------------------------------------------------------------------------------------------
+ * Text segment: BM25 over device-resident postings
+ * (reference: tantivy TopDocs::order_by_score called at nidx_text/src/reader.rs:433-435 and
+ *  nidx_paragraph/src/reader.rs:290-292; statistics over the union of segments,
+ *  nidx_tantivy/src/index_reader.rs:39-77)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nidx_txt_segment nidx_txt_segment;
+
+#define NIDX_BM25_OR 0   /* nidx_paragraph keyword query: Occur::Should (keyword_parser.rs:62-67) */
+#define NIDX_BM25_AND 1  /* nidx_text: QueryParser::set_conjunction_by_default (reader.rs:372-377) */
+
+/* Postings in CSR form: term_off[n_terms+1], post_doc/post_tf[term_off[n_terms]] (doc ids ascending
+ * per term), fieldnorm_id[n_docs] (tantivy's 1-byte fieldnorm code).  Host pointers; copied to HBM. */
+int nidx_txt_create(int32_t device, uint32_t n_docs, uint32_t n_terms, const uint64_t* term_off, const uint32_t* post_doc,
+                    const uint32_t* post_tf, const uint8_t* fieldnorm_id, nidx_txt_segment** out);
+/* Collection statistics of the whole index (all segments, all GPUs): total docs, total tokens,
+ * doc_freq[n_terms].  Defaults to the segment's own statistics. */
+int nidx_txt_set_stats(nidx_txt_segment* seg, uint64_t total_docs, uint64_t total_tokens, const uint64_t* doc_freq);
+int nidx_txt_set_alive(nidx_txt_segment* seg, const uint64_t* alive_bits);
+void nidx_txt_close(nidx_txt_segment* seg);
+
+typedef struct nidx_txt_search_params {
+    int32_t k;       /* result_per_page + 1 in the reference (reader.rs:386-387) */
+    int32_t mode;    /* NIDX_BM25_* */
+    int32_t use_tf;  /* 0: IndexRecordOption::Basic (tf == 1), 1: real term frequencies */
+    float min_score; /* results below are dropped after top-k (reader.rs:302-305) */
+} nidx_txt_search_params;
+
+/* nq queries; query i is query_terms[query_off[i] .. query_off[i+1]) (term ids).
+ * out_docs/out_scores [nq][k] (score desc, then doc asc), out_counts[nq], out_total[nq] = number of
+ * matching documents (the Count collector, reader.rs:433).  `mem` applies to queries and outputs. */
+int nidx_txt_search(nidx_txt_segment* seg, const uint32_t* query_terms, const uint32_t* query_off, int32_t nq, int mem,
+                    const nidx_txt_search_params* p, uint32_t* out_docs, float* out_scores, int32_t* out_counts, uint64_t* out_total,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIDX_B200_H */

@@ -1,0 +1,1003 @@
+// nidx_b200 — C ABI (include/nidx_b200.h) over the CUDA kernels.  Host side of the hot path:
+// what nidx_vector's OpenSegment / HnswBuilder and the tantivy collector call do on the CPU in the
+// reference is orchestrated here on one GPU.  No CPU fallback: every entry point needs a device.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nidx_b200.h"
+#include "bm25.cuh"
+#include "common.cuh"
+#include "hnsw_build.cuh"
+#include "hnsw_search.cuh"
+#include "scan.cu"
+#include "segment_io.hpp"
+#include "topk.cuh"
+
+using namespace nidx;
+
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(expr)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess) return fail(NIDX_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+static int ilog2(int x) { int b = 0; while ((1 << b) < x) ++b; return b; }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) return fail(NIDX_ECUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+#define ENSURE(buf, bytes) do { int r__ = (buf).ensure(bytes); if (r__) return r__; } while (0)
+
+// Per-call scratch; a segment keeps a pool so concurrent searches do not share one.
+struct Workspace {
+    DevBuf queries, qnorms, out_ids, out_scores, out_counts, scores, partial, filter, misc, sched;
+    cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool busy = false;
+    ~Workspace() {
+        queries.release(); qnorms.release(); out_ids.release(); out_scores.release(); out_counts.release();
+        scores.release(); partial.release(); filter.release(); misc.release(); sched.release();
+        if (done) cudaEventDestroy(done);
+    }
+};
+
+struct WorkspacePool {
+    std::mutex mu;
+    std::vector<Workspace*> all;
+    Workspace* acquire(cudaStream_t stream) {
+        std::lock_guard<std::mutex> g(mu);
+        for (Workspace* w : all)
+            if (!w->busy) {
+                w->busy = true;
+                if (w->last_stream != stream && w->done) cudaEventSynchronize(w->done);
+                return w;
+            }
+        Workspace* w = new Workspace();
+        cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming);
+        w->busy = true;
+        all.push_back(w);
+        return w;
+    }
+    void release(Workspace* w, cudaStream_t stream) {
+        cudaEventRecord(w->done, stream);
+        std::lock_guard<std::mutex> g(mu);
+        w->last_stream = stream;
+        w->busy = false;
+    }
+    ~WorkspacePool() { for (Workspace* w : all) delete w; }
+};
+struct WsGuard {
+    WorkspacePool& pool; Workspace* w; cudaStream_t s;
+    WsGuard(WorkspacePool& p, cudaStream_t st) : pool(p), w(p.acquire(st)), s(st) {}
+    ~WsGuard() { pool.release(w, s); }
+};
+
+struct nidx_vec_segment {
+    nidx_vec_config cfg;
+    uint64_t n = 0;
+    int d = 0, ld = 0;
+    int sm_count = 0;
+    float* d_vecs = nullptr;
+    float* d_norms = nullptr;
+    uint32_t* d_par_of = nullptr;
+    uint32_t* d_par_first = nullptr;
+    uint32_t n_par = 0;
+    uint64_t* d_alive = nullptr;
+    // graph
+    bool has_graph = false;
+    std::vector<uint8_t> h_level;
+    uint8_t* d_level = nullptr;
+    uint32_t entry_node = 0, entry_layer = 0;
+    int s0 = 0, su = 0;
+    uint64_t upper_rows = 0;
+    uint32_t* d_adj0 = nullptr; float* d_w0 = nullptr;
+    uint64_t* d_upper_off = nullptr;
+    uint32_t* d_adjU = nullptr; float* d_wU = nullptr;
+    unsigned long long* d_counters = nullptr;  // [4]
+    unsigned int* d_work_counter = nullptr;
+    WorkspacePool pool;
+
+    VecDev vdev() const {
+        VecDev v;
+        v.vecs = d_vecs; v.norms = d_norms; v.paragraph_of = d_par_of; v.n = (uint32_t)n; v.d = d; v.ld = ld; v.sim = cfg.similarity;
+        return v;
+    }
+    GraphDev gdev() const {
+        GraphDev g;
+        g.n = (uint32_t)n; g.M = cfg.m; g.M0 = cfg.m0; g.s0 = s0; g.su = su; g.level = d_level;
+        g.entry_node = entry_node; g.entry_layer = entry_layer;
+        g.adj0 = d_adj0; g.w0 = d_w0; g.upper_off = d_upper_off; g.adjU = d_adjU; g.wU = d_wU;
+        return g;
+    }
+};
+
+static int stride0_for(int M0) { return (M0 + 31) / 32 * 32; }
+static int strideU_for(int M) { return (M + 15) / 16 * 16; }
+
+static void free_graph(nidx_vec_segment* s) {
+    cudaFree(s->d_level); cudaFree(s->d_adj0); cudaFree(s->d_w0); cudaFree(s->d_upper_off); cudaFree(s->d_adjU); cudaFree(s->d_wU);
+    s->d_level = nullptr; s->d_adj0 = nullptr; s->d_w0 = nullptr; s->d_upper_off = nullptr; s->d_adjU = nullptr; s->d_wU = nullptr;
+    s->has_graph = false;
+}
+
+// Allocate graph storage for the given levels (ram_hnsw.rs:88-107: every node in layers 0..=level,
+// entry point in the top layer -- lowest id there).
+static int alloc_graph(nidx_vec_segment* s, const uint8_t* level) {
+    free_graph(s);
+    uint64_t n = s->n;
+    s->h_level.assign(level, level + n);
+    std::vector<uint64_t> off(n ? n : 1);
+    uint64_t rows = 0;
+    uint32_t top = 0;
+    for (uint64_t i = 0; i < n; ++i) { off[i] = rows; rows += level[i]; top = std::max<uint32_t>(top, level[i]); }
+    s->upper_rows = rows;
+    s->entry_layer = top;
+    s->entry_node = 0;
+    for (uint64_t i = 0; i < n; ++i) if (level[i] == top) { s->entry_node = (uint32_t)i; break; }
+    s->s0 = stride0_for(s->cfg.m0);
+    s->su = strideU_for(s->cfg.m);
+    size_t n0 = (size_t)n * s->s0, nu = (size_t)std::max<uint64_t>(rows, 1) * s->su;
+    CU(cudaMalloc(&s->d_level, std::max<uint64_t>(n, 1)));
+    CU(cudaMalloc(&s->d_adj0, n0 * 4 + 16));
+    CU(cudaMalloc(&s->d_w0, n0 * 4 + 16));
+    CU(cudaMalloc(&s->d_upper_off, std::max<uint64_t>(n, 1) * 8));
+    CU(cudaMalloc(&s->d_adjU, nu * 4));
+    CU(cudaMalloc(&s->d_wU, nu * 4));
+    CU(cudaMemcpy(s->d_level, level, n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s->d_upper_off, off.data(), n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemset(s->d_adj0, 0xFF, n0 * 4));
+    CU(cudaMemset(s->d_w0, 0, n0 * 4));
+    CU(cudaMemset(s->d_adjU, 0xFF, nu * 4));
+    CU(cudaMemset(s->d_wU, 0, nu * 4));
+    return 0;
+}
+
+extern "C" {
+
+const char* nidx_last_error(void) { return g_err.c_str(); }
+int nidx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+uint64_t nidx_launch_count(void) { return g_launches.load(); }
+
+static int check_device(int device) {
+    int n = nidx_device_count();
+    if (n <= 0) return fail(NIDX_ENODEVICE, "no CUDA device available (nidx_b200 has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(NIDX_EINVAL, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+static int fill_defaults(nidx_vec_config* c) {
+    if (c->dimension <= 0) return fail(NIDX_EINVAL, "dimension must be positive");
+    if (c->similarity != NIDX_SIM_DOT && c->similarity != NIDX_SIM_COSINE) return fail(NIDX_EINVAL, "unknown similarity %d", c->similarity);
+    if (c->m <= 0) c->m = 30;                              // params.rs:40
+    if (c->m0 <= 0) c->m0 = 60;                            // params.rs:34
+    if (c->ef_construction <= 0) c->ef_construction = 100; // params.rs:43
+    if (c->ef_search <= 0) c->ef_search = 30;              // params.rs:46
+    if (c->m0 > HS_MAX_ROW || c->m > HS_MAX_ROW) return fail(NIDX_EINVAL, "M / M0 above %d not supported", HS_MAX_ROW);
+    if (c->ef_construction > HB_MAX_CAND) return fail(NIDX_EINVAL, "ef_construction above %d not supported", HB_MAX_CAND);
+    return 0;
+}
+
+// Common tail of create/open: vectors are in d_vecs; compute norms, paragraph CSR.
+static int finish_create(nidx_vec_segment* s, const uint32_t* paragraph_of_host) {
+    uint64_t n = s->n;
+    CU(cudaMalloc(&s->d_norms, std::max<uint64_t>(n, 1) * 4));
+    if (n) {
+        int blocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)s->sm_count * 16);
+        row_norms_kernel<<<blocks, 256>>>(s->d_vecs, s->ld, n, s->d_norms);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+    s->n_par = (uint32_t)n;
+    if (paragraph_of_host) {
+        // paragraphs own contiguous vector ranges (data_store/v2: first_vector / num_vectors)
+        std::vector<uint32_t> first;
+        uint32_t prev = NIDX_NIL;
+        for (uint64_t i = 0; i < n; ++i) {
+            uint32_t p = paragraph_of_host[i];
+            if (i == 0 || p != prev) {
+                if (p != (uint32_t)first.size()) return fail(NIDX_EINVAL, "paragraph_of must be contiguous and ascending from 0 (vector %llu -> %u)", (unsigned long long)i, p);
+                first.push_back((uint32_t)i);
+                prev = p;
+            }
+        }
+        first.push_back((uint32_t)n);
+        s->n_par = (uint32_t)first.size() - 1;
+        if (s->n_par != n) {  // only materialise when some paragraph has several vectors
+            CU(cudaMalloc(&s->d_par_of, n * 4));
+            CU(cudaMemcpy(s->d_par_of, paragraph_of_host, n * 4, cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&s->d_par_first, first.size() * 4));
+            CU(cudaMemcpy(s->d_par_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    CU(cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
+    CU(cudaMemset(s->d_counters, 0, 4 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&s->d_work_counter, 64));
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+static int new_segment(const nidx_vec_config* cfg, nidx_vec_segment** out) {
+    if (!cfg || !out) return fail(NIDX_EINVAL, "null argument");
+    nidx_vec_config c = *cfg;
+    int r = fill_defaults(&c);
+    if (r) return r;
+    r = check_device(c.device);
+    if (r) return r;
+    nidx_vec_segment* s = new nidx_vec_segment();
+    s->cfg = c;
+    s->d = c.dimension;
+    s->ld = (c.dimension + 3) / 4 * 4;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, c.device);
+    s->sm_count = prop.multiProcessorCount;
+    *out = s;
+    return 0;
+}
+
+int nidx_vec_create(const nidx_vec_config* cfg, const float* vectors, uint64_t n, int32_t ld, int mem, const uint32_t* paragraph_of,
+                    nidx_vec_segment** out) {
+    nidx_vec_segment* s = nullptr;
+    int r = new_segment(cfg, &s);
+    if (r) return r;
+    if (n >= (1ull << 31)) { delete s; return fail(NIDX_EINVAL, "at most 2^31-1 vectors per segment"); }
+    if (ld < s->d) { delete s; return fail(NIDX_EINVAL, "ld %d < dimension %d (VectorErr::InconsistentDimensions)", ld, s->d); }
+    s->n = n;
+    r = [&]() -> int {
+        CU(cudaMalloc(&s->d_vecs, std::max<size_t>((size_t)n * s->ld * 4, 16)));
+        if (n == 0) return 0;
+        if (mem == NIDX_MEM_HOST && ld == s->ld) {
+            CU(cudaMemcpy(s->d_vecs, vectors, (size_t)n * ld * 4, cudaMemcpyHostToDevice));
+        } else if (mem == NIDX_MEM_DEVICE && ld == s->ld) {
+            CU(cudaMemcpy(s->d_vecs, vectors, (size_t)n * ld * 4, cudaMemcpyDeviceToDevice));
+        } else {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(vectors);
+            void* staged = nullptr;
+            if (mem == NIDX_MEM_HOST) {
+                CU(cudaMalloc(&staged, (size_t)n * ld * 4));
+                CU(cudaMemcpy(staged, vectors, (size_t)n * ld * 4, cudaMemcpyHostToDevice));
+                src = reinterpret_cast<const unsigned char*>(staged);
+            }
+            pad_rows_kernel<<<s->sm_count * 8, 256>>>(src, (size_t)ld * 4, s->d, s->d_vecs, s->ld, n);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+            if (staged) cudaFree(staged);
+        }
+        return 0;
+    }();
+    if (!r) r = finish_create(s, paragraph_of);
+    if (r) { nidx_vec_close(s); return r; }
+    *out = s;
+    return 0;
+}
+
+void nidx_vec_close(nidx_vec_segment* s) {
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    cudaDeviceSynchronize();
+    free_graph(s);
+    cudaFree(s->d_vecs); cudaFree(s->d_norms); cudaFree(s->d_par_of); cudaFree(s->d_par_first); cudaFree(s->d_alive);
+    cudaFree(s->d_counters); cudaFree(s->d_work_counter);
+    delete s;
+}
+
+uint64_t nidx_vec_len(const nidx_vec_segment* s) { return s ? s->n : 0; }
+const float* nidx_vec_device_vectors(const nidx_vec_segment* s, int32_t* ld_out) {
+    if (!s) return nullptr;
+    if (ld_out) *ld_out = s->ld;
+    return s->d_vecs;
+}
+
+int nidx_vec_set_alive(nidx_vec_segment* s, const uint64_t* alive_bits, int mem) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(s->cfg.device));
+    if (!alive_bits) { cudaFree(s->d_alive); s->d_alive = nullptr; return 0; }
+    size_t words = ((size_t)s->n_par + 63) / 64;
+    if (!s->d_alive) CU(cudaMalloc(&s->d_alive, std::max<size_t>(words, 1) * 8));
+    CU(cudaMemcpy(s->d_alive, alive_bits, words * 8, mem == NIDX_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int nidx_vec_graph_dims(const nidx_vec_segment* s, int32_t* s0, int32_t* su, uint64_t* upper_rows, uint32_t* entry_node, uint32_t* entry_layer) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    if (!s->has_graph) return fail(NIDX_ESTATE, "segment has no HNSW graph");
+    if (s0) *s0 = s->s0;
+    if (su) *su = s->su;
+    if (upper_rows) *upper_rows = s->upper_rows;
+    if (entry_node) *entry_node = s->entry_node;
+    if (entry_layer) *entry_layer = s->entry_layer;
+    return 0;
+}
+
+int nidx_vec_set_graph(nidx_vec_segment* s, const uint8_t* level, const uint32_t* adj0, const float* w0, const uint32_t* adjU, const float* wU) {
+    if (!s || !level || !adj0) return fail(NIDX_EINVAL, "null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    for (uint64_t i = 0; i < s->n; ++i)
+        if (level[i] >= HS_MAX_LAYERS) return fail(NIDX_EINVAL, "node %llu has level %d >= %d", (unsigned long long)i, level[i], HS_MAX_LAYERS);
+    int r = alloc_graph(s, level);
+    if (r) return r;
+    size_t n0 = (size_t)s->n * s->s0, nu = (size_t)s->upper_rows * s->su;
+    CU(cudaMemcpy(s->d_adj0, adj0, n0 * 4, cudaMemcpyHostToDevice));
+    if (w0) CU(cudaMemcpy(s->d_w0, w0, n0 * 4, cudaMemcpyHostToDevice));
+    if (nu && adjU) CU(cudaMemcpy(s->d_adjU, adjU, nu * 4, cudaMemcpyHostToDevice));
+    if (nu && wU) CU(cudaMemcpy(s->d_wU, wU, nu * 4, cudaMemcpyHostToDevice));
+    s->has_graph = true;
+    return 0;
+}
+
+int nidx_vec_get_graph(const nidx_vec_segment* s, uint8_t* level, uint32_t* adj0, float* w0, uint32_t* adjU, float* wU) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    if (!s->has_graph) return fail(NIDX_ESTATE, "segment has no HNSW graph");
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaDeviceSynchronize());
+    size_t n0 = (size_t)s->n * s->s0, nu = (size_t)s->upper_rows * s->su;
+    if (level) memcpy(level, s->h_level.data(), s->n);
+    if (adj0) CU(cudaMemcpy(adj0, s->d_adj0, n0 * 4, cudaMemcpyDeviceToHost));
+    if (w0) CU(cudaMemcpy(w0, s->d_w0, n0 * 4, cudaMemcpyDeviceToHost));
+    if (adjU && nu) CU(cudaMemcpy(adjU, s->d_adjU, nu * 4, cudaMemcpyDeviceToHost));
+    if (wU && nu) CU(cudaMemcpy(wU, s->d_wU, nu * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int nidx_vec_counters(nidx_vec_segment* s, uint64_t out[3]) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(s->cfg.device));
+    unsigned long long h[4];
+    CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2] + h[3];
+    return 0;
+}
+
+// ---- search -----------------------------------------------------------------------------------
+// segment.rs:626-660 (dense f32: no RaBitQ).
+static bool use_hnsw_cost(size_t total_nodes, size_t matching_nodes, size_t top_k, size_t M) {
+    float l = logf((float)total_nodes) - 2.0f;
+    float hnsw_rq = l * l * logf((float)top_k);
+    size_t hnsw_full = top_k * M * total_nodes / std::max<size_t>(matching_nodes, 1);
+    size_t hnsw_cost = (size_t)(hnsw_rq < 0 ? 0 : hnsw_rq) + hnsw_full;
+    return hnsw_cost < matching_nodes;
+}
+
+__global__ void and_bits_kernel(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t words, unsigned long long* count) {
+    unsigned long long local = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t v = a[i] & (b ? b[i] : ~0ull);
+        out[i] = v;
+        local += __popcll(v);
+    }
+    for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list_cap, int* cu_cap, int* hash_bits, size_t* bytes) {
+    int cu = std::min(std::max(ef0 + 4 * s->s0, 2 * ef0), 4096);
+    int lc = std::max(ef0, cu);
+    int slots = next_pow2(std::max(2048, (ef0 * s->s0 * 3) / 2));
+    slots = std::max(slots, next_pow2(4 * lc));
+    *list_cap = lc; *cu_cap = cu; *hash_bits = ilog2(slots);
+    *bytes = hs_smem_bytes(s->ld, lc, *hash_bits);
+    if (*bytes > 200 * 1024) return fail(NIDX_EINVAL, "HNSW search needs %zu bytes of shared memory (ef=%d, k=%d, dim=%d): too large", *bytes, ef0, k, s->d);
+    return 0;
+}
+
+int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p, uint32_t* out_ids,
+                    float* out_scores, int32_t* out_counts, void* stream_) {
+    if (!s || !p || (!queries && nq > 0) || !out_ids || !out_scores) return fail(NIDX_EINVAL, "null argument");
+    if (nq <= 0) return 0;
+    if (ldq < s->d) return fail(NIDX_EINVAL, "query dimension %d != index dimension %d (VectorErr::InconsistentDimensions)", ldq, s->d);
+    int k = p->k;
+    if (k <= 0) return fail(NIDX_EINVAL, "k must be positive");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    WsGuard g(s->pool, stream);
+    Workspace& w = *g.w;
+    bool host = mem == NIDX_MEM_HOST;
+    VecDev V = s->vdev();
+
+    // queries -> [nq][ld] zero padded on device, norms
+    ENSURE(w.queries, (size_t)nq * s->ld * 4);
+    ENSURE(w.qnorms, (size_t)nq * 4);
+    float* dq = w.queries.as<float>();
+    if (ldq == s->ld) {
+        CU(cudaMemcpyAsync(dq, queries, (size_t)nq * ldq * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+    } else {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(queries);
+        if (host) {
+            ENSURE(w.misc, (size_t)nq * ldq * 4);
+            CU(cudaMemcpyAsync(w.misc.p, queries, (size_t)nq * ldq * 4, cudaMemcpyHostToDevice, stream));
+            src = w.misc.as<unsigned char>();
+        }
+        pad_rows_kernel<<<std::min(nq, 1024), 256, 0, stream>>>(src, (size_t)ldq * 4, s->d, dq, s->ld, (uint64_t)nq);
+        LAUNCHED();
+    }
+    if (s->cfg.similarity == NIDX_SIM_COSINE) {
+        row_norms_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(dq, s->ld, (uint64_t)nq, w.qnorms.as<float>());
+        LAUNCHED();
+    }
+
+    // filter ∧ alive (segment.rs:516-534)
+    const uint64_t* bits = s->d_alive;
+    size_t words = ((size_t)s->n_par + 63) / 64;
+    uint64_t matching = s->n_par;
+    if (p->filter_bits) {
+        ENSURE(w.filter, words * 8 * 2 + 64);
+        uint64_t* d_in = w.filter.as<uint64_t>();
+        uint64_t* d_out = d_in + words;
+        unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_out + words);
+        const uint64_t* fsrc = p->filter_bits;
+        if (host) { CU(cudaMemcpyAsync(d_in, p->filter_bits, words * 8, cudaMemcpyHostToDevice, stream)); fsrc = d_in; }
+        CU(cudaMemsetAsync(d_cnt, 0, 8, stream));
+        and_bits_kernel<<<std::min<size_t>((words + 255) / 256, 1024), 256, 0, stream>>>(fsrc, s->d_alive, d_out, words, d_cnt);
+        LAUNCHED();
+        bits = d_out;
+        matching = p->filter_matching;
+        if (p->method == NIDX_METHOD_AUTO && matching == 0) {
+            unsigned long long h = 0;
+            CU(cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            matching = h;
+        }
+    }
+
+    int method = p->method;
+    if (method == NIDX_METHOD_AUTO) {
+        if (!s->has_graph) method = NIDX_METHOD_BRUTE;
+        else if (matching == 0 && p->filter_bits) method = NIDX_METHOD_BRUTE;
+        else method = use_hnsw_cost(s->n_par, matching, (size_t)k, (size_t)s->cfg.m) ? NIDX_METHOD_HNSW : NIDX_METHOD_BRUTE;
+    }
+    if (method == NIDX_METHOD_HNSW && !s->has_graph) return fail(NIDX_ESTATE, "HNSW search requested but the segment has no graph");
+
+    // outputs
+    uint32_t* d_ids = out_ids; float* d_sc = out_scores; int* d_cnt = out_counts;
+    if (host || !out_counts) {
+        ENSURE(w.out_ids, (size_t)nq * k * 4);
+        ENSURE(w.out_scores, (size_t)nq * k * 4);
+        ENSURE(w.out_counts, (size_t)nq * 4);
+        if (host) { d_ids = w.out_ids.as<uint32_t>(); d_sc = w.out_scores.as<float>(); }
+        if (host || !out_counts) d_cnt = w.out_counts.as<int>();
+    }
+
+    if (s->n == 0) {
+        CU(cudaMemsetAsync(d_ids, 0xFF, (size_t)nq * k * 4, stream));
+        CU(cudaMemsetAsync(d_sc, 0, (size_t)nq * k * 4, stream));
+        CU(cudaMemsetAsync(d_cnt, 0, (size_t)nq * 4, stream));
+    } else if (method == NIDX_METHOD_BRUTE) {
+        if (k > 1024) return fail(NIDX_EINVAL, "brute-force k above 1024 not supported");
+        int cap = topk_cap(k, 256);
+        int n_chunks = (int)std::min<uint64_t>(std::max<uint64_t>(1, ((uint64_t)s->sm_count * 4 + nq - 1) / nq), (s->n_par + 4095) / 4096);
+        n_chunks = std::max(n_chunks, 1);
+        // bound the score matrix: process queries in groups
+        size_t max_score_bytes = (size_t)4 << 30;
+        int qgroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, max_score_bytes / ((size_t)s->n * 4)));
+        qgroup = std::max(SCAN_QT, qgroup / SCAN_QT * SCAN_QT);
+        qgroup = std::min(qgroup, (nq + SCAN_QT - 1) / SCAN_QT * SCAN_QT);
+        ENSURE(w.scores, (size_t)qgroup * s->n * 4);
+        ENSURE(w.partial, (size_t)qgroup * n_chunks * k * 8);
+        size_t smem_scan = (size_t)SCAN_QT * s->ld * 4;
+        if (smem_scan > 48 * 1024) CU(cudaFuncSetAttribute(scan_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+        if ((size_t)cap * 8 > 48 * 1024) {
+            CU(cudaFuncSetAttribute(scan_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
+            CU(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
+        }
+        for (int q0 = 0; q0 < nq; q0 += qgroup) {
+            int nqg = std::min(qgroup, nq - q0);
+            int n_qtiles = (nqg + SCAN_QT - 1) / SCAN_QT;
+            uint64_t n_vchunks = (s->n + SCAN_WARPS * SCAN_VPW - 1) / (SCAN_WARPS * SCAN_VPW);
+            uint64_t grid = n_vchunks * n_qtiles;
+            if (grid > 0x7FFFFFFFull) return fail(NIDX_EINVAL, "scan grid too large");
+            scan_scores_kernel<<<(unsigned)grid, SCAN_WARPS * 32, smem_scan, stream>>>(V, dq + (size_t)q0 * s->ld, w.qnorms.as<float>() + q0, nqg, n_qtiles,
+                                                                                     w.scores.as<float>());
+            LAUNCHED();
+            scan_select_kernel<<<dim3(n_chunks, nqg), 256, (size_t)cap * 8, stream>>>(w.scores.as<float>(), (uint32_t)s->n, s->n_par, s->d_par_first, nullptr, bits,
+                                                                                      p->min_score, k, cap, n_chunks, w.partial.as<uint64_t>());
+            LAUNCHED();
+            topk_merge_kernel<<<nqg, 256, (size_t)cap * 8, stream>>>(w.partial.as<uint64_t>(), n_chunks * k, k, cap, d_ids + (size_t)q0 * k, d_sc + (size_t)q0 * k,
+                                                                    d_cnt + q0);
+            LAUNCHED();
+        }
+        CU(cudaGetLastError());
+    } else {
+        int ef = p->ef > 0 ? p->ef : s->cfg.ef_search;
+        int ef0 = std::max(k, ef);  // search.rs:338-345
+        int list_cap, cu_cap, hash_bits;
+        size_t smem;
+        int r = hnsw_search_smem(s, ef0, k, &list_cap, &cu_cap, &hash_bits, &smem);
+        if (r) return r;
+        SearchArgs a;
+        memset(&a, 0, sizeof(a));
+        a.mode = 0; a.nq = nq; a.queries = dq; a.qnorms = w.qnorms.as<float>(); a.k = k; a.ef0 = ef0; a.min_score = p->min_score;
+        a.with_duplicates = p->with_duplicates; a.multi_vector = s->cfg.multi_vector; a.filter = bits;
+        a.out_ids = d_ids; a.out_scores = d_sc; a.out_counts = d_cnt;
+        a.hash_bits = hash_bits; a.list_cap = list_cap; a.cu_cap = cu_cap;
+        // the scheduler counter lives in the workspace: concurrent calls must not share it
+        ENSURE(w.sched, 64);
+        a.work_counter = w.sched.as<unsigned int>();
+        a.counters = s->d_counters;
+        CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
+        CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+        CU(cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hnsw_search_kernel, HS_THREADS, smem));
+        int grid = std::min(nq, std::max(1, occ) * s->sm_count);
+        hnsw_search_kernel<<<grid, HS_THREADS, smem, stream>>>(V, s->gdev(), a);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+
+    if (host) {
+        CU(cudaMemcpyAsync(out_ids, d_ids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_scores, d_sc, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+        if (out_counts) CU(cudaMemcpyAsync(out_counts, d_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int32_t nq, int32_t k, uint32_t* out_ids,
+                    float* out_scores, int32_t* out_part, void* stream_) {
+    int r = check_device(device);
+    if (r) return r;
+    if (!ids || !scores || !out_ids || !out_scores || n_parts <= 0 || nq <= 0 || k <= 0) return fail(NIDX_EINVAL, "bad argument");
+    if (k > 1024 || (long long)n_parts * k >= (1ll << 31)) return fail(NIDX_EINVAL, "k above 1024 not supported");
+    int cap = topk_cap(k, 256);
+    if ((size_t)cap * 8 > 48 * 1024) CU(cudaFuncSetAttribute(parts_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
+    parts_merge_kernel<<<nq, 256, (size_t)cap * 8, reinterpret_cast<cudaStream_t>(stream_)>>>(ids, scores, n_parts, nq, k, cap, out_ids, out_scores, out_part);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- build ------------------------------------------------------------------------------------
+// Level RNG: build.rs:40,97-101.  rand 0.10 SmallRng = xoshiro256++ seeded by SplitMix64 [recalled].
+static void host_assign_levels(uint64_t n, int M, uint64_t seed, uint8_t* level) {
+    uint64_t st[4], state = seed;
+    for (int i = 0; i < 4; ++i) {
+        state += 0x9e3779b97f4a7c15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        st[i] = z ^ (z >> 31);
+    }
+    auto rotl = [](uint64_t x, int k) { return (x << k) | (x >> (64 - k)); };
+    double level_factor = 1.0 / std::log((double)M);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t r = rotl(st[0] + st[3], 23) + st[0];
+        uint64_t t = st[1] << 17;
+        st[2] ^= st[0]; st[3] ^= st[1]; st[1] ^= st[2]; st[0] ^= st[3];
+        st[2] ^= t;
+        st[3] = rotl(st[3], 45);
+        double u = (double)(r >> 12) * (1.0 / 4503599627370496.0);
+        double lv = std::round(-std::log(u) * level_factor);
+        if (!(lv < (double)(HS_MAX_LAYERS - 1))) lv = (double)(HS_MAX_LAYERS - 1);
+        level[i] = (uint8_t)lv;
+    }
+}
+
+int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, void* stream_) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    uint64_t n = s->n;
+    if (max_batch <= 0) max_batch = 4096;
+    std::vector<uint8_t> level(n ? n : 1);
+    host_assign_levels(n, s->cfg.m, seed, level.data());
+    int r = alloc_graph(s, level.data());
+    if (r) return r;
+    s->has_graph = true;
+    if (n == 0) return 0;
+
+    // insertion order: entry point first, then ascending id; batch b = min(max_batch, max(1, done/16))
+    std::vector<uint32_t> order(n);
+    order[0] = s->entry_node;
+    for (uint64_t i = 0, j = 1; i < n; ++i) if (i != s->entry_node) order[j++] = (uint32_t)i;
+    std::vector<uint32_t> ends;
+    for (uint64_t done = 0; done < n;) {
+        uint64_t b = std::min<uint64_t>({(uint64_t)max_batch, std::max<uint64_t>(1, done / 16), n - done});
+        done += b;
+        ends.push_back((uint32_t)done);
+    }
+    // work items (node position, layer), insertion order, layer ascending
+    std::vector<uint64_t> wstart(n + 1);
+    uint64_t W = 0;
+    for (uint64_t i = 0; i < n; ++i) { wstart[i] = W; W += (uint64_t)level[order[i]] + 1; }
+    wstart[n] = W;
+    std::vector<uint32_t> w_pos(W);
+    std::vector<unsigned char> w_layer(W);
+    for (uint64_t i = 0; i < n; ++i)
+        for (int l = 0; l <= level[order[i]]; ++l) { w_pos[wstart[i] + l] = (uint32_t)i; w_layer[wstart[i] + l] = (unsigned char)l; }
+    uint64_t max_b = 0, max_w = 0;
+    for (size_t b = 0, begin = 0; b < ends.size(); begin = ends[b], ++b) {
+        max_b = std::max<uint64_t>(max_b, ends[b] - begin);
+        max_w = std::max<uint64_t>(max_w, wstart[ends[b]] - wstart[begin]);
+    }
+    int efC = s->cfg.ef_construction, M = s->cfg.m;
+    uint32_t *d_order = nullptr, *d_wpos = nullptr, *d_rev_x = nullptr, *d_idx = nullptr, *d_idx_sorted = nullptr;
+    unsigned char* d_wlayer = nullptr;
+    uint64_t *d_found = nullptr, *d_rev_key = nullptr, *d_key_sorted = nullptr;
+    int* d_found_count = nullptr;
+    float* d_rev_sim = nullptr;
+    void* d_cub = nullptr;
+    size_t cub_bytes = 0;
+    size_t max_rev = (size_t)max_w * M;
+    auto cleanup = [&]() {
+        cudaFree(d_order); cudaFree(d_wpos); cudaFree(d_wlayer); cudaFree(d_found); cudaFree(d_found_count); cudaFree(d_rev_key); cudaFree(d_rev_x);
+        cudaFree(d_rev_sim); cudaFree(d_key_sorted); cudaFree(d_idx); cudaFree(d_idx_sorted); cudaFree(d_cub);
+    };
+    r = [&]() -> int {
+        CU(cudaMalloc(&d_order, n * 4));
+        CU(cudaMalloc(&d_wpos, W * 4));
+        CU(cudaMalloc(&d_wlayer, W));
+        CU(cudaMalloc(&d_found, (size_t)max_b * HS_MAX_LAYERS * efC * 8));
+        CU(cudaMalloc(&d_found_count, (size_t)max_b * HS_MAX_LAYERS * 4));
+        CU(cudaMalloc(&d_rev_key, max_rev * 8));
+        CU(cudaMalloc(&d_key_sorted, max_rev * 8));
+        CU(cudaMalloc(&d_rev_x, max_rev * 4));
+        CU(cudaMalloc(&d_rev_sim, max_rev * 4));
+        CU(cudaMalloc(&d_idx, max_rev * 4));
+        CU(cudaMalloc(&d_idx_sorted, max_rev * 4));
+        CU(cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(d_wpos, w_pos.data(), W * 4, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(d_wlayer, w_layer.data(), W, cudaMemcpyHostToDevice, stream));
+        {
+            std::vector<uint32_t> iota(max_rev);
+            for (size_t i = 0; i < max_rev; ++i) iota[i] = (uint32_t)i;
+            CU(cudaMemcpyAsync(d_idx, iota.data(), max_rev * 4, cudaMemcpyHostToDevice, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, d_rev_key, d_key_sorted, d_idx, d_idx_sorted, (int)max_rev, 0, 40, stream));
+        CU(cudaMalloc(&d_cub, cub_bytes));
+
+        // shared-memory plans
+        int ef0 = efC;
+        int list_cap = efC, hash_bits;
+        int slots = next_pow2(std::max(2048, (efC * s->s0 * 3) / 2));
+        slots = std::max(slots, next_pow2(4 * list_cap));
+        hash_bits = ilog2(slots);
+        size_t smem_search = hs_smem_bytes(s->ld, list_cap, hash_bits);
+        if (smem_search > 200 * 1024) return fail(NIDX_EINVAL, "HNSW build search needs %zu bytes of shared memory", smem_search);
+        CU(cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hnsw_search_kernel, HS_THREADS, smem_search));
+        size_t row_bytes = (size_t)s->ld * 4;
+        size_t budget = 96 * 1024;
+        int cache_sel = (int)std::min<size_t>(M, budget / row_bytes);
+        int prune_max = std::max(s->cfg.m0, M) * 95 / 100;
+        int cache_rev = (int)std::min<size_t>(prune_max, budget / row_bytes);
+        size_t smem_sel = hb_smem_bytes(s->ld, cache_sel), smem_rev = hb_smem_bytes(s->ld, cache_rev);
+        CU(cudaFuncSetAttribute(select_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+        CU(cudaFuncSetAttribute(reverse_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rev));
+        CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+        (void)ef0;
+
+        VecDev V = s->vdev();
+        GraphDev G = s->gdev();
+        uint32_t begin = 0;
+        for (size_t b = 0; b < ends.size(); ++b) {
+            uint32_t end = ends[b];
+            int nb = (int)(end - begin);
+            int nw = (int)(wstart[end] - wstart[begin]);
+            SearchArgs a;
+            memset(&a, 0, sizeof(a));
+            a.mode = 1; a.nq = nb; a.nodes = d_order + begin; a.efC = efC; a.found = d_found; a.found_count = d_found_count;
+            a.hash_bits = hash_bits; a.list_cap = list_cap; a.cu_cap = 0; a.work_counter = s->d_work_counter; a.counters = s->d_counters;
+            CU(cudaMemsetAsync(s->d_work_counter, 0, 4, stream));
+            int grid = std::min(nb, std::max(1, occ) * s->sm_count);
+            hnsw_search_kernel<<<grid, HS_THREADS, smem_search, stream>>>(V, G, a);
+            LAUNCHED();
+            BuildArgs ba;
+            ba.n_work = nw; ba.w_pos = d_wpos + wstart[begin]; ba.w_layer = d_wlayer + wstart[begin]; ba.order = d_order; ba.batch_begin = begin;
+            ba.efC = efC; ba.M = M; ba.found = d_found; ba.found_count = d_found_count; ba.rev_key = d_rev_key; ba.rev_x = d_rev_x; ba.rev_sim = d_rev_sim;
+            ba.cache_cap = cache_sel;
+            select_link_kernel<<<nw, HB_THREADS, smem_sel, stream>>>(V, G, ba);
+            LAUNCHED();
+            int n_rev = nw * M;
+            size_t tmp = cub_bytes;
+            CU(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_rev_key, d_key_sorted, d_idx, d_idx_sorted, n_rev, 0, 40, stream));
+            LAUNCHED();
+            ReverseArgs ra;
+            ra.n_rev = n_rev; ra.key_sorted = d_key_sorted; ra.idx_sorted = d_idx_sorted; ra.rev_x = d_rev_x; ra.rev_sim = d_rev_sim; ra.cache_cap = cache_rev;
+            reverse_link_kernel<<<n_rev, HB_THREADS, smem_rev, stream>>>(V, G, ra);
+            LAUNCHED();
+            begin = end;
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(stream));
+        return 0;
+    }();
+    cleanup();
+    if (r) { free_graph(s); return r; }
+    return 0;
+}
+
+// ---- segment files ----------------------------------------------------------------------------
+int nidx_vec_open(const nidx_vec_config* cfg, const char* dir, nidx_vec_segment** out) {
+    if (!dir) return fail(NIDX_EINVAL, "null dir");
+    nidx_vec_segment* s = nullptr;
+    int r = new_segment(cfg, &s);
+    if (r) return r;
+    std::string err;
+    std::vector<unsigned char> raw;
+    if (!segio::read_file(std::string(dir) + "/vectors.bin", raw, err)) { delete s; return fail(NIDX_EIO, "%s", err.c_str()); }
+    size_t rec = (size_t)s->d * 4 + 4;  // vector_store.rs:33-68: [dim x f32 LE][paragraph_addr u32]
+    if (raw.size() % rec) { delete s; return fail(NIDX_EIO, "vectors.bin size %zu is not a multiple of the record length %zu", raw.size(), rec); }
+    uint64_t n = raw.size() / rec;
+    s->n = n;
+    std::vector<uint32_t> par(n);
+    for (uint64_t i = 0; i < n; ++i) memcpy(&par[i], raw.data() + i * rec + (size_t)s->d * 4, 4);
+    r = [&]() -> int {
+        CU(cudaMalloc(&s->d_vecs, std::max<size_t>((size_t)n * s->ld * 4, 16)));
+        if (n) {
+            void* staged = nullptr;
+            CU(cudaMalloc(&staged, raw.size()));
+            CU(cudaMemcpy(staged, raw.data(), raw.size(), cudaMemcpyHostToDevice));
+            pad_rows_kernel<<<s->sm_count * 8, 256>>>(reinterpret_cast<unsigned char*>(staged), rec, s->d, s->d_vecs, s->ld, n);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+            cudaFree(staged);
+        }
+        return 0;
+    }();
+    if (!r) r = finish_create(s, n ? par.data() : nullptr);
+    if (r) { nidx_vec_close(s); return r; }
+    // hnsw.graph (+ hnsw.edges) if present
+    std::vector<unsigned char> graph, edges;
+    if (segio::read_file(std::string(dir) + "/hnsw.graph", graph, err) && !graph.empty()) {
+        segio::read_file(std::string(dir) + "/hnsw.edges", edges, err);
+        segio::FlatGraph fg;
+        if (!segio::parse_graph_v2(graph, edges, n, stride0_for(s->cfg.m0), strideU_for(s->cfg.m), HS_MAX_LAYERS, fg, err)) {
+            nidx_vec_close(s);
+            return fail(NIDX_EIO, "hnsw.graph: %s", err.c_str());
+        }
+        r = nidx_vec_set_graph(s, fg.level.data(), fg.adj0.data(), fg.w0.empty() ? nullptr : fg.w0.data(), fg.adjU.data(), fg.wU.empty() ? nullptr : fg.wU.data());
+        if (r) { nidx_vec_close(s); return r; }
+        s->entry_node = fg.entry_node;   // the file's entry point (ram_hnsw.rs: hash-order dependent in the reference)
+        s->entry_layer = fg.entry_layer;
+    }
+    *out = s;
+    return 0;
+}
+
+int nidx_vec_save(nidx_vec_segment* s, const char* dir) {
+    if (!s || !dir) return fail(NIDX_EINVAL, "null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaDeviceSynchronize());
+    uint64_t n = s->n;
+    std::vector<float> vecs((size_t)n * s->ld);
+    CU(cudaMemcpy(vecs.data(), s->d_vecs, vecs.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> par(n);
+    if (s->d_par_of) CU(cudaMemcpy(par.data(), s->d_par_of, n * 4, cudaMemcpyDeviceToHost));
+    else for (uint64_t i = 0; i < n; ++i) par[i] = (uint32_t)i;
+    std::string err;
+    if (!segio::write_vectors_bin(std::string(dir) + "/vectors.bin", vecs.data(), n, s->d, s->ld, par.data(), err)) return fail(NIDX_EIO, "%s", err.c_str());
+    if (s->has_graph) {
+        segio::FlatGraph fg;
+        fg.n = n; fg.s0 = s->s0; fg.su = s->su; fg.entry_node = s->entry_node; fg.entry_layer = s->entry_layer;
+        fg.level = s->h_level;
+        fg.upper_rows = s->upper_rows;
+        fg.adj0.resize((size_t)n * s->s0); fg.w0.resize((size_t)n * s->s0);
+        fg.adjU.resize((size_t)s->upper_rows * s->su); fg.wU.resize((size_t)s->upper_rows * s->su);
+        int r = nidx_vec_get_graph(s, nullptr, fg.adj0.data(), fg.w0.data(), fg.adjU.data(), fg.wU.data());
+        if (r) return r;
+        if (!segio::write_graph_v2(std::string(dir) + "/hnsw.graph", std::string(dir) + "/hnsw.edges", fg, err)) return fail(NIDX_EIO, "%s", err.c_str());
+    }
+    return 0;
+}
+
+// ---- text ---------------------------------------------------------------------------------------
+struct nidx_txt_segment {
+    int device = 0, sm_count = 0;
+    uint32_t n_docs = 0, n_terms = 0;
+    uint64_t n_post = 0;
+    uint64_t* d_term_off = nullptr;
+    uint32_t* d_doc = nullptr;
+    uint32_t* d_tf = nullptr;
+    unsigned char* d_fieldnorm = nullptr;
+    uint64_t* d_alive = nullptr;
+    float* d_weight = nullptr;   // [n_terms]
+    float* d_norm_cache = nullptr;  // [256]
+    std::vector<uint64_t> own_df;
+    uint64_t own_tokens = 0;
+    float max_weight = 0.0f;
+    std::vector<float> h_weight;
+    WorkspacePool pool;
+};
+
+// tantivy fieldnorm code -> token count (Lucene SmallFloat.byte4ToInt) [recalled]
+static uint32_t fieldnorm_id_to_value(uint32_t id) {
+    if (id < 24) return id;
+    uint32_t j = id - 24, bits = j & 7, shift = j >> 3;
+    return 24 + (shift == 0 ? bits : ((bits | 8u) << (shift - 1)));
+}
+
+static int txt_upload_stats(nidx_txt_segment* t, uint64_t total_docs, uint64_t total_tokens, const uint64_t* df) {
+    const float K1 = 1.2f, B = 0.75f;
+    float avg = (float)total_tokens / (float)total_docs;
+    float cache[256];
+    for (int i = 0; i < 256; ++i) cache[i] = K1 * (1.0f - B + B * (float)fieldnorm_id_to_value(i) / avg);
+    t->h_weight.resize(t->n_terms);
+    for (uint32_t i = 0; i < t->n_terms; ++i) {
+        float x = ((float)(total_docs - df[i]) + 0.5f) / ((float)df[i] + 0.5f);
+        t->h_weight[i] = logf(1.0f + x) * (1.0f + K1);
+    }
+    CU(cudaMemcpy(t->d_norm_cache, cache, sizeof(cache), cudaMemcpyHostToDevice));
+    if (t->n_terms) CU(cudaMemcpy(t->d_weight, t->h_weight.data(), (size_t)t->n_terms * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int nidx_txt_create(int32_t device, uint32_t n_docs, uint32_t n_terms, const uint64_t* term_off, const uint32_t* post_doc, const uint32_t* post_tf,
+                    const uint8_t* fieldnorm_id, nidx_txt_segment** out) {
+    if (!term_off || !fieldnorm_id || !out) return fail(NIDX_EINVAL, "null argument");
+    int r = check_device(device);
+    if (r) return r;
+    if (n_docs >= (1u << 31)) return fail(NIDX_EINVAL, "at most 2^31-1 documents per segment");
+    nidx_txt_segment* t = new nidx_txt_segment();
+    t->device = device; t->n_docs = n_docs; t->n_terms = n_terms; t->n_post = term_off[n_terms];
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    t->sm_count = prop.multiProcessorCount;
+    r = [&]() -> int {
+        CU(cudaMalloc(&t->d_term_off, ((size_t)n_terms + 1) * 8));
+        CU(cudaMalloc(&t->d_doc, std::max<uint64_t>(t->n_post, 1) * 4));
+        CU(cudaMalloc(&t->d_tf, std::max<uint64_t>(t->n_post, 1) * 4));
+        CU(cudaMalloc(&t->d_fieldnorm, std::max<uint32_t>(n_docs, 1)));
+        CU(cudaMalloc(&t->d_weight, std::max<uint32_t>(n_terms, 1) * 4));
+        CU(cudaMalloc(&t->d_norm_cache, 1024));
+        CU(cudaMemcpy(t->d_term_off, term_off, ((size_t)n_terms + 1) * 8, cudaMemcpyHostToDevice));
+        if (t->n_post) {
+            CU(cudaMemcpy(t->d_doc, post_doc, t->n_post * 4, cudaMemcpyHostToDevice));
+            if (post_tf) CU(cudaMemcpy(t->d_tf, post_tf, t->n_post * 4, cudaMemcpyHostToDevice));
+        }
+        CU(cudaMemcpy(t->d_fieldnorm, fieldnorm_id, n_docs, cudaMemcpyHostToDevice));
+        t->own_df.resize(n_terms);
+        for (uint32_t i = 0; i < n_terms; ++i) t->own_df[i] = term_off[i + 1] - term_off[i];
+        // a segment alone only knows the quantised lengths; the exact token total comes with set_stats
+        uint64_t tokens = 0;
+        for (uint32_t i = 0; i < n_docs; ++i) tokens += fieldnorm_id_to_value(fieldnorm_id[i]);
+        t->own_tokens = tokens;
+        return txt_upload_stats(t, std::max<uint32_t>(n_docs, 1), std::max<uint64_t>(tokens, 1), t->own_df.data());
+    }();
+    if (r) { nidx_txt_close(t); return r; }
+    *out = t;
+    return 0;
+}
+
+int nidx_txt_set_stats(nidx_txt_segment* t, uint64_t total_docs, uint64_t total_tokens, const uint64_t* doc_freq) {
+    if (!t || !total_docs) return fail(NIDX_EINVAL, "bad argument");
+    CU(cudaSetDevice(t->device));
+    return txt_upload_stats(t, total_docs, total_tokens, doc_freq ? doc_freq : t->own_df.data());
+}
+
+int nidx_txt_set_alive(nidx_txt_segment* t, const uint64_t* alive_bits) {
+    if (!t) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(t->device));
+    if (!alive_bits) { cudaFree(t->d_alive); t->d_alive = nullptr; return 0; }
+    size_t words = ((size_t)t->n_docs + 63) / 64;
+    if (!t->d_alive) CU(cudaMalloc(&t->d_alive, std::max<size_t>(words, 1) * 8));
+    CU(cudaMemcpy(t->d_alive, alive_bits, words * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void nidx_txt_close(nidx_txt_segment* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaDeviceSynchronize();
+    cudaFree(t->d_term_off); cudaFree(t->d_doc); cudaFree(t->d_tf); cudaFree(t->d_fieldnorm); cudaFree(t->d_alive); cudaFree(t->d_weight);
+    cudaFree(t->d_norm_cache);
+    delete t;
+}
+
+int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint32_t* query_off, int32_t nq, int mem, const nidx_txt_search_params* p,
+                    uint32_t* out_docs, float* out_scores, int32_t* out_counts, uint64_t* out_total, void* stream_) {
+    if (!t || !p || !query_off || !out_docs || !out_scores || !out_counts) return fail(NIDX_EINVAL, "null argument");
+    if (nq <= 0) return 0;
+    int k = p->k;
+    if (k <= 0 || k > 1024) return fail(NIDX_EINVAL, "k must be in 1..1024");
+    CU(cudaSetDevice(t->device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    bool host = mem == NIDX_MEM_HOST;
+    WsGuard g(t->pool, stream);
+    Workspace& w = *g.w;
+    // query offsets are needed on the host to size things
+    std::vector<uint32_t> h_off(nq + 1);
+    if (host) memcpy(h_off.data(), query_off, ((size_t)nq + 1) * 4);
+    else { CU(cudaMemcpyAsync(h_off.data(), query_off, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, stream)); CU(cudaStreamSynchronize(stream)); }
+    uint32_t n_qt = h_off[nq];
+    int max_terms = 0;
+    for (int i = 0; i < nq; ++i) max_terms = std::max<int>(max_terms, h_off[i + 1] - h_off[i]);
+    if (max_terms > BM_MAX_TERMS) return fail(NIDX_EINVAL, "queries with more than %d terms are not supported", BM_MAX_TERMS);
+    const uint32_t *d_qt = query_terms, *d_qo = query_off;
+    if (host) {
+        ENSURE(w.queries, ((size_t)n_qt + nq + 1) * 4 + 16);
+        uint32_t* base = w.queries.as<uint32_t>();
+        CU(cudaMemcpyAsync(base, query_off, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, stream));
+        if (n_qt) CU(cudaMemcpyAsync(base + nq + 1, query_terms, (size_t)n_qt * 4, cudaMemcpyHostToDevice, stream));
+        d_qo = base; d_qt = base + nq + 1;
+    }
+    // fixed-point scale: the largest possible sum is max_terms * max term weight (tf factor < 1)
+    float wmax = 0.0f;
+    for (float x : t->h_weight) wmax = std::max(wmax, x);
+    float bound = std::max(1.0f, wmax * (float)std::max(max_terms, 1));
+    int shift = 24;
+    while (shift > 4 && bound * (float)(1u << shift) >= 4.0e9f) --shift;
+
+    int cap = topk_cap(k, BM_THREADS);
+    int tile = 16384;
+    size_t smem = bm_smem_bytes(tile, cap);
+    ENSURE(w.partial, (size_t)nq * k * 8);
+    ENSURE(w.misc, (size_t)nq * 8);
+    uint32_t* d_docs = out_docs; float* d_sc = out_scores; int* d_cnt = out_counts;
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(out_total);
+    if (host) {
+        ENSURE(w.out_ids, (size_t)nq * k * 4);
+        ENSURE(w.out_scores, (size_t)nq * k * 4);
+        ENSURE(w.out_counts, (size_t)nq * 4);
+        d_docs = w.out_ids.as<uint32_t>(); d_sc = w.out_scores.as<float>(); d_cnt = w.out_counts.as<int>();
+        d_total = w.misc.as<unsigned long long>();
+    }
+    TxtDev T;
+    T.n_docs = t->n_docs; T.n_terms = t->n_terms; T.term_off = t->d_term_off; T.post_doc = t->d_doc; T.post_tf = t->d_tf; T.fieldnorm = t->d_fieldnorm;
+    T.alive = t->d_alive;
+    Bm25Args a;
+    a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.mode = p->mode; a.use_tf = p->use_tf; a.k = k; a.cap = cap; a.tile = tile;
+    a.term_weight = t->d_weight; a.norm_cache = t->d_norm_cache; a.shift = shift; a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total;
+    CU(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bm25_kernel<<<nq, BM_THREADS, smem, stream>>>(T, a);
+    LAUNCHED();
+    bm25_finish_kernel<<<nq, 128, 0, stream>>>(w.partial.as<uint64_t>(), nq, k, p->min_score, d_docs, d_sc, d_cnt);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    if (host) {
+        CU(cudaMemcpyAsync(out_docs, d_docs, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_scores, d_sc, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_counts, d_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+        if (out_total) CU(cudaMemcpyAsync(out_total, d_total, (size_t)nq * 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+}  // extern "C"

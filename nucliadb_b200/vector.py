@@ -1,0 +1,419 @@
+"""Host-side mirror of ``nidx_vector``'s public interface over the CUDA library.
+
+Same names, argument meaning and error behaviour as the reference's Rust API for the search hot
+path (``nidx/nidx_vector/src/lib.rs:65-148``):
+
+* ``VectorConfig``            config.rs:102-124 (+ the HNSW constants of hnsw/params.rs as fields)
+* ``VectorSearchRequest``     request_types.rs:18-35
+* ``VectorSearcher.open / .search``   lib.rs:124-139 -> searcher.rs:241-343
+* ``VectorIndexer.index_elems / .merge``  lib.rs:69-117 -> segment.rs:92-286 (Elem level; protobuf
+  ``Resource`` decoding is outside the hot path)
+* ``OpenSegment``             segment.rs:428-567
+
+All arithmetic (similarities, top-k, graph walks, graph construction) runs in ``libnidx_b200.so`` on
+the GPU; this module only keeps the per-paragraph metadata (ids, labels) the reference keeps in
+``paragraphs.bin`` and evaluates filter formulas to bitsets (inverted_index/paragraph.rs:124-186).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import uuid as _uuid
+from dataclasses import dataclass, field
+from typing import Iterable, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import NIL, NidxError, VecConfig, VecSearchParams, check, ptr
+
+
+class Similarity(enum.Enum):  # config.rs:33-37
+    Cosine = "Cosine"
+    Dot = "Dot"
+
+
+class VectorCardinality(enum.Enum):  # config.rs
+    Single = "Single"
+    Multi = "Multi"
+
+
+class FilterOperator(enum.Enum):  # nidx_types/src/prefilter.rs
+    And = "And"
+    Or = "Or"
+
+
+@dataclass
+class VectorConfig:
+    """config.rs:102-124.  ``m/m0/ef_construction/ef_search`` are the compile-time constants of
+    hnsw/params.rs:34-46 made per-index (defaults = the reference's values)."""
+    dimension: int
+    similarity: Similarity = Similarity.Cosine
+    normalize_vectors: bool = False
+    vector_cardinality: VectorCardinality = VectorCardinality.Single
+    flags: list = field(default_factory=list)
+    m: int = 30
+    m0: int = 60
+    ef_construction: int = 100
+    ef_search: int = 30
+    device: int = 0
+
+    def _c(self) -> VecConfig:
+        return VecConfig(self.dimension, _lib.NIDX_SIM_COSINE if self.similarity == Similarity.Cosine else _lib.NIDX_SIM_DOT,
+                         int(self.vector_cardinality == VectorCardinality.Multi), self.m, self.m0, self.ef_construction, self.ef_search,
+                         self.device)
+
+
+# ---- nidx_types::query_language::BooleanExpression ----------------------------------------------
+@dataclass(frozen=True)
+class Literal:
+    value: str
+
+
+@dataclass(frozen=True)
+class Not:
+    operand: "BooleanExpression"
+
+
+@dataclass(frozen=True)
+class Operation:
+    operator: str  # "and" | "or"
+    operands: tuple
+
+
+BooleanExpression = Union[Literal, Not, Operation]
+
+
+@dataclass(frozen=True)
+class FieldId:  # nidx_types/src/prefilter.rs
+    resource_id: _uuid.UUID
+    field_id: Optional[str] = None  # e.g. "/a/title"
+
+
+class PrefilterResult:
+    """nidx_types/src/prefilter.rs: All | None | Some(fields)."""
+
+    def __init__(self, kind: str, fields: Sequence[FieldId] = ()):
+        self.kind, self.fields = kind, list(fields)
+
+    @classmethod
+    def all(cls):
+        return cls("all")
+
+    @classmethod
+    def none(cls):
+        return cls("none")
+
+    @classmethod
+    def some(cls, fields):
+        return cls("some", fields)
+
+
+@dataclass
+class VectorSearchRequest:  # request_types.rs:18-35 (Default: min_score 0.0, with_duplicates false)
+    vector: Sequence[float] = ()
+    result_per_page: int = 0
+    with_duplicates: bool = False
+    vector_set: str = ""
+    min_score: float = 0.0
+    filtering_formula: Optional[BooleanExpression] = None
+    segment_filtering_formula: Optional[BooleanExpression] = None
+    filter_operator: FilterOperator = FilterOperator.And
+
+
+@dataclass
+class DocumentScored:  # nodereader.proto:126-135
+    doc_id: str
+    score: float
+    labels: list
+    metadata: Optional[bytes]
+
+
+@dataclass
+class VectorSearchResponse:
+    documents: list
+
+
+@dataclass
+class Elem:  # segment.rs Elem {key, vectors, metadata, labels}
+    key: str
+    vectors: Sequence[Sequence[float]]
+    labels: Sequence[str] = ()
+    metadata: Optional[bytes] = None
+
+
+# ---- formula.rs ------------------------------------------------------------------------------------
+@dataclass
+class _KeyPrefixSet:
+    keys: frozenset
+
+
+def _map_expression(e):  # query_io.rs:20-50
+    return e
+
+
+def field_key(field_id: str) -> Optional[bytes]:
+    """utils.rs:80-117 FieldKey::from_field_id: 16 raw uuid bytes [+ type + "/" + name]."""
+    parts = field_id.split("/")
+    try:
+        rid = _uuid.UUID(parts[0])
+    except ValueError:
+        return None
+    if len(parts) >= 2:
+        if len(parts) >= 3:
+            return rid.bytes + parts[1].encode() + b"/" + parts[2].encode()
+        return None
+    return rid.bytes
+
+
+def _labels_key(label: str) -> str:  # inverted_index/paragraph.rs:64-66
+    return label[1:] + "/"
+
+
+class OpenSegment:
+    """segment.rs OpenSegment: device-resident vectors + graph, host-resident paragraph metadata."""
+
+    def __init__(self, config: VectorConfig, handle, keys, labels, metadata, first_vec, tags=frozenset()):
+        self.config = config
+        self._h = handle
+        self.keys, self.labels, self.metadata = list(keys), [tuple(l) for l in labels], list(metadata)
+        self.first_vec = np.asarray(first_vec, dtype=np.uint32)  # [n_par + 1]
+        self.records = len(self.keys)
+        self.tags = frozenset(tags)
+        self.alive = np.ones(self.records, dtype=bool)
+        self._field_keys = [field_key(k) for k in self.keys]
+        self._label_index: dict = {}
+        for p, ls in enumerate(self.labels):
+            for l in ls:
+                self._label_index.setdefault(_labels_key(l), []).append(p)
+        self._field_index: dict = {}
+        for p, fk in enumerate(self._field_keys):
+            if fk is not None:
+                self._field_index.setdefault(fk, []).append(p)
+
+    # -- lifecycle -----------------------------------------------------------------------------
+    @classmethod
+    def create(cls, elems: Sequence[Elem], config: VectorConfig, tags=frozenset(), build_graph=True, seed=2, max_batch=4096):
+        """segment::create (segment.rs:199-286): data store + HNSW (GPU build)."""
+        L = _lib.require_device()
+        dim = config.dimension
+        vecs, par_of, first = [], [], [0]
+        for p, e in enumerate(elems):
+            if config.vector_cardinality == VectorCardinality.Single and len(e.vectors) != 1:
+                raise NidxError(-1, "single-vector index got an element with several vectors")
+            for v in e.vectors:
+                if len(v) != dim:
+                    raise NidxError(-1, f"InconsistentDimensions: index_config {dim}, vector {len(v)}")
+                vecs.append(np.asarray(v, dtype=np.float32))
+                par_of.append(p)
+            first.append(len(vecs))
+        arr = np.stack(vecs).astype(np.float32) if vecs else np.zeros((0, dim), dtype=np.float32)
+        if config.normalize_vectors and len(arr):  # indexer.rs:94-146 normalises at index time (utils.rs:20-23)
+            mag = np.sqrt(np.add.reduce(arr.astype(np.float32) ** 2, axis=1, dtype=np.float32))
+            arr = (arr / mag[:, None]).astype(np.float32)
+        par = np.asarray(par_of, dtype=np.uint32)
+        h = C.c_void_p()
+        cfg = config._c()
+        check(L.nidx_vec_create(C.byref(cfg), ptr(arr), C.c_uint64(len(arr)), C.c_int32(dim), _lib.NIDX_MEM_HOST, ptr(par) if len(par) else None,
+                                C.byref(h)))
+        seg = cls(config, h, [e.key for e in elems], [e.labels for e in elems], [e.metadata for e in elems], first, tags)
+        seg.host_vectors = arr
+        if build_graph and len(arr):
+            check(L.nidx_vec_build_hnsw(h, C.c_uint64(seed), C.c_int32(max_batch), None))
+        return seg
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().nidx_vec_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- deletions (segment.rs:428-445, lib.rs:166-200) -------------------------------------------
+    def apply_deletions(self, deleted_keys: Iterable[str]):
+        for k in deleted_keys:
+            fk = field_key(k)
+            if fk is None:
+                continue
+            for stored, paragraphs in self._field_index.items():  # prefix match (ids_for_deletion_key)
+                if stored.startswith(fk):
+                    self.alive[paragraphs] = False
+        bits = np.packbits(self.alive, bitorder="little")
+        words = np.zeros((self.records + 63) // 64 * 8, dtype=np.uint8)
+        words[: len(bits)] = bits
+        check(_lib.load().nidx_vec_set_alive(self._h, ptr(words.view(np.uint64)), _lib.NIDX_MEM_HOST))
+
+    # -- filters (inverted_index/paragraph.rs:124-186) ---------------------------------------------
+    def _clause(self, clause) -> np.ndarray:
+        out = np.zeros(self.records, dtype=bool)
+        if isinstance(clause, Literal):
+            prefix = _labels_key(clause.value)
+            for k, ps in self._label_index.items():
+                if k.startswith(prefix):
+                    out[ps] = True
+            return out
+        if isinstance(clause, _KeyPrefixSet):
+            for fid in clause.keys:
+                fk = field_key(fid)
+                if fk is not None and fk in self._field_index:  # exact get (fst_index.rs:71-73)
+                    out[self._field_index[fk]] = True
+            return out
+        if isinstance(clause, Not):
+            return ~self._clause(clause.operand)
+        if isinstance(clause, Operation):
+            parts = [self._clause(c) for c in clause.operands]
+            acc = parts[0]
+            for p in parts[1:]:
+                acc = (acc & p) if clause.operator == "and" else (acc | p)
+            return acc
+        raise TypeError(f"unknown clause {clause!r}")
+
+    def filter_bitset(self, clauses, operator_and=True) -> Optional[np.ndarray]:
+        if not clauses:
+            return None
+        acc = self._clause(clauses[0])
+        for c in clauses[1:]:
+            acc = (acc & self._clause(c)) if operator_and else (acc | self._clause(c))
+        return acc
+
+    # -- search (segment.rs:477-567) ---------------------------------------------------------------
+    def search(self, query, clauses, operator_and, with_duplicates, top_k, min_score, method=_lib.NIDX_METHOD_AUTO, ef=0):
+        """-> (vector addrs [<=k], scores) for one query."""
+        ids, scores, counts = self.search_batch(np.asarray(query, dtype=np.float32)[None, :], top_k, min_score, with_duplicates, clauses, operator_and,
+                                                method, ef)
+        c = int(counts[0])
+        return ids[0, :c], scores[0, :c]
+
+    def search_batch(self, queries: np.ndarray, top_k, min_score=0.0, with_duplicates=False, clauses=(), operator_and=True,
+                     method=_lib.NIDX_METHOD_AUTO, ef=0):
+        L = _lib.load()
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq, dim = queries.shape
+        if dim != self.config.dimension:
+            raise NidxError(-1, f"InconsistentDimensions: index_config {self.config.dimension}, vector {dim}")
+        ids = np.empty((nq, top_k), dtype=np.uint32)
+        scores = np.empty((nq, top_k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        p = VecSearchParams(top_k, ef, min_score, int(with_duplicates), method, None, 0)
+        keep = None
+        mask = self.filter_bitset(list(clauses), operator_and)
+        if mask is not None:
+            matching = int((mask & self.alive).sum())
+            if matching == 0:  # segment.rs:531-534
+                ids.fill(NIL)
+                scores.fill(0)
+                counts.fill(0)
+                return ids, scores, counts
+            bits = np.packbits(mask, bitorder="little")
+            keep = np.zeros((self.records + 63) // 64 * 8, dtype=np.uint8)
+            keep[: len(bits)] = bits
+            p.filter_bits = keep.ctypes.data
+            p.filter_matching = matching
+        check(L.nidx_vec_search(self._h, ptr(queries), C.c_int32(nq), C.c_int32(dim), _lib.NIDX_MEM_HOST, C.byref(p), ptr(ids), ptr(scores), ptr(counts),
+                                None))
+        return ids, scores, counts
+
+    def paragraph_of(self, vector_addr: int) -> int:
+        return int(np.searchsorted(self.first_vec, vector_addr, side="right") - 1)
+
+
+def _segment_matches(expr, tags) -> bool:  # searcher.rs segment_matches
+    if isinstance(expr, Literal):
+        return expr.value in tags
+    if isinstance(expr, Not):
+        return not _segment_matches(expr.operand, tags)
+    vals = [_segment_matches(o, tags) for o in expr.operands]
+    return all(vals) if expr.operator == "and" else any(vals)
+
+
+class _Fssc:
+    """searcher.rs:150-199 fixed-size sorted collection keyed by paragraph id."""
+
+    def __init__(self, size, with_duplicates):
+        self.size, self.with_duplicates = size, with_duplicates
+        self.seen, self.buff = set(), {}
+
+    def add(self, pid, score, payload, vector_bytes):
+        if not self.with_duplicates:
+            if vector_bytes in self.seen:
+                return
+            self.seen.add(vector_bytes)
+        if len(self.buff) == self.size:
+            smaller = [(s, k) for k, (s, _) in self.buff.items() if score > s]
+            if smaller:
+                _, victim = min(smaller, key=lambda t: t[0])
+                del self.buff[victim]
+                self.buff.setdefault(pid, (score, payload))
+        else:
+            self.buff.setdefault(pid, (score, payload))
+
+    def result(self):
+        return sorted(((s, k, p) for k, (s, p) in self.buff.items()), key=lambda t: -t[0])
+
+
+class VectorSearcher:
+    """lib.rs:124-139 + searcher.rs:241-343."""
+
+    def __init__(self, config: VectorConfig, segments: Sequence[OpenSegment]):
+        self.config, self.open_segments = config, list(segments)
+
+    @classmethod
+    def open(cls, config: VectorConfig, segments: Sequence[tuple], deletions: Sequence[tuple] = ()):
+        """segments: [(OpenSegment, seq)], deletions: [(key, seq)]; a deletion applies to a segment
+        iff del.seq > segment.seq (lib.rs:188-199)."""
+        _lib.require_device()
+        opened = []
+        for seg, seq in segments:
+            dels = [k for k, dseq in deletions if dseq > seq]
+            if dels:
+                seg.apply_deletions(dels)
+            opened.append(seg)
+        return cls(config, opened)
+
+    def search(self, request: VectorSearchRequest, prefilter: PrefilterResult = None, method=_lib.NIDX_METHOD_AUTO, ef=0) -> VectorSearchResponse:
+        prefilter = prefilter or PrefilterResult.all()
+        clauses = []
+        if prefilter.kind == "some":  # searcher.rs:300-314
+            clauses.append(_KeyPrefixSet(frozenset(f"{f.resource_id.hex}{f.field_id}" if f.field_id else f.resource_id.hex for f in prefilter.fields)))
+        if request.filtering_formula is not None:
+            clauses.append(_map_expression(request.filtering_formula))
+        operator_and = request.filter_operator == FilterOperator.And
+        query = np.asarray(request.vector, dtype=np.float32)
+        if self.config.normalize_vectors:  # searcher.rs:246-252, utils.rs:20-23
+            mag = np.float32(0)
+            for x in query:
+                mag = np.float32(mag + np.float32(x) * np.float32(x))
+            query = (query / np.sqrt(mag)).astype(np.float32)
+        if len(query) != self.config.dimension:
+            raise NidxError(-1, f"InconsistentDimensions: index_config {self.config.dimension}, vector {len(query)}")
+        k = request.result_per_page
+        fssc = _Fssc(k, request.with_duplicates)
+        if k > 0 and prefilter.kind != "none":
+            for seg in self.open_segments:
+                if request.segment_filtering_formula is not None and not _segment_matches(request.segment_filtering_formula, seg.tags):
+                    continue
+                addrs, scores = seg.search(query, clauses, operator_and, request.with_duplicates, k, request.min_score, method, ef)
+                for a, s in zip(addrs, scores):
+                    p = seg.paragraph_of(int(a))
+                    vb = (id(seg), int(a)) if request.with_duplicates else self._vector_bytes(seg, int(a))
+                    fssc.add(seg.keys[p], float(s), (seg, p), vb)
+        docs = [DocumentScored(pid, score, list(seg.labels[p]), seg.metadata[p]) for score, pid, (seg, p) in fssc.result()]
+        return VectorSearchResponse(docs)
+
+    @staticmethod
+    def _vector_bytes(seg: OpenSegment, addr: int) -> bytes:
+        # Fssc's exact-duplicate test hashes the raw vector bytes (searcher.rs:175-183); the host copy
+        # kept at create/open time plays the role of the reference's mmap of vectors.bin.
+        return seg.host_vectors[addr].tobytes()
+
+
+class VectorIndexer:
+    """lib.rs:65-117 at Elem granularity."""
+
+    @staticmethod
+    def index_elems(elems: Sequence[Elem], config: VectorConfig, tags=frozenset(), **kw) -> OpenSegment:
+        return OpenSegment.create(elems, config, tags, **kw)

@@ -1,0 +1,124 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import make_queries, make_vectors
+from nucliadb_b200 import _lib
+from nucliadb_b200.segment import VectorSegment
+
+pytestmark = pytest.mark.gpu
+
+
+def _seg(v, sim, **kw):
+    return VectorSegment.create(v, v.shape[1], similarity=sim, **kw)
+
+
+@pytest.mark.parametrize("sim", [_lib.NIDX_SIM_COSINE, _lib.NIDX_SIM_DOT])
+@pytest.mark.parametrize("d", [128, 100, 384])
+def test_brute_force_matches_oracle(sim, d):
+    v = make_vectors(5000, d, seed=5)
+    if sim == _lib.NIDX_SIM_DOT:
+        v = v * np.linspace(0.5, 1.5, len(v), dtype=np.float32)[:, None]
+    q = make_queries(v, 37)
+    seg = _seg(v, sim)
+    ids, sc, cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+    oi, os_, oc = O.brute_force(v, q, 10, sim=sim, nthreads=4)
+    assert (cnt == oc).all()
+    assert (ids == oi).all()                      # ids bit-exact
+    assert np.array_equal(sc, os_)                # same summation order => scores bit-exact
+    assert np.abs(sc - os_).max() <= 1e-5         # the stated tolerance
+
+
+def test_brute_force_min_score_and_alive():
+    v = make_vectors(3000, 64, seed=6)
+    q = make_queries(v, 8)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE)
+    alive = np.ones(3000, dtype=bool)
+    alive[::3] = False
+    words = np.zeros((3000 + 63) // 64 * 8, dtype=np.uint8)
+    pb = np.packbits(alive, bitorder="little")
+    words[: len(pb)] = pb
+    bits = words.view(np.uint64)
+    seg.set_alive(bits)
+    ids, sc, cnt = seg.search(q, 20, min_score=0.5, method=_lib.NIDX_METHOD_BRUTE)
+    oi, os_, oc = O.brute_force(v, q, 20, min_score=0.5, alive_bits=bits)
+    assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+    assert all(alive[i] for i in ids[ids != 0xFFFFFFFF])
+
+
+def test_hnsw_search_matches_oracle_on_oracle_graph(small_data):
+    v, q = small_data
+    g = O.hnsw_build(v, M=16, M0=32, efC=100, max_batch=64, nthreads=8)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=100)
+    seg.set_graph(g.level, g.adj0, g.adjU, g.w0, g.wU)
+    for ef in (30, 128):
+        ids, sc, cnt = seg.search(q, 10, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+        oi, os_, oc, counters = O.hnsw_search(v, g, q, 10, ef, nthreads=8)
+        assert (cnt == oc).all()
+        assert (ids == oi).all()                  # same graph, same walk => identical ids
+        assert np.array_equal(sc, os_)
+        c = seg.counters()
+        assert c["overflows"] == 0
+        assert c["similarities"] == counters[0] and c["expansions"] == counters[1]
+
+
+def test_hnsw_search_with_dedup_and_filter(small_data):
+    v, q = small_data
+    v = v.copy()
+    v[1000:1010] = v[0:10]          # exact duplicates
+    g = O.hnsw_build(v, M=16, M0=32, efC=100, max_batch=64, nthreads=8)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=100)
+    seg.set_graph(g.level, g.adj0, g.adjU)
+    keep = np.random.default_rng(3).random(len(v)) < 0.3
+    words = np.zeros((len(v) + 63) // 64 * 8, dtype=np.uint8)
+    pb = np.packbits(keep, bitorder="little")
+    words[: len(pb)] = pb
+    bits = words.view(np.uint64)
+    qq = np.concatenate([q[:16], v[0:10]])
+    ids, sc, cnt = seg.search(qq, 10, ef=64, min_score=0.0, with_duplicates=False, method=_lib.NIDX_METHOD_HNSW, filter_bits=bits)
+    oi, os_, oc, _ = O.hnsw_search(v, g, qq, 10, 64, min_score=0.0, with_duplicates=False, filter_bits=bits, nthreads=4)
+    assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+
+
+def test_gpu_build_recall_and_invariants():
+    v = make_vectors(30000, 96, seed=11)
+    q = make_queries(v, 200)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=100)
+    seg.build_hnsw(seed=2, max_batch=1024)
+    assert seg.counters()["overflows"] == 0
+    g = seg.get_graph()
+    # structural invariants (hnsw/params.rs:24-31): degree caps, targets in range and in the layer
+    deg0 = (g["adj0"] != 0xFFFFFFFF).sum(1)
+    assert deg0.max() <= 32 and deg0.min() >= 1
+    assert (g["level"] == O.assign_levels(len(v), 16, 2)).all()
+    valid = g["adj0"][g["adj0"] != 0xFFFFFFFF]
+    assert valid.max() < len(v)
+    bi, _, _ = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+    for ef, floor in ((30, 0.90), (128, 0.98)):
+        hi, _, _ = seg.search(q, 10, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+        rec = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(hi, bi)])
+        print("gpu-built graph recall@10 ef", ef, rec)
+        assert rec >= floor
+    # the oracle searching the GPU-built graph agrees with the GPU searching it
+    og = O.Graph(len(v), 16, 32, g["level"])
+    og.adj0[:], og.adjU[:] = g["adj0"], g["adjU"][: og.adjU.shape[0]]
+    og.entry_node, og.entry_layer = g["entry_node"], g["entry_layer"]
+    hi, hs, _ = seg.search(q, 10, ef=64, method=_lib.NIDX_METHOD_HNSW)
+    oi, os_, _, _ = O.hnsw_search(v, og, q, 10, 64, nthreads=8)
+    assert (hi == oi).all() and np.array_equal(hs, os_)
+
+
+def test_gpu_build_equals_oracle_batch_build():
+    """Same levels, same batch schedule, same arithmetic order => the same graph, edge for edge."""
+    v = make_vectors(4000, 64, seed=12)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=8, m0=16, ef_construction=40)
+    seg.build_hnsw(seed=2, max_batch=128)
+    g = seg.get_graph()
+    og = O.hnsw_build(v, M=8, M0=16, efC=40, seed=2, max_batch=128, nthreads=8)
+    assert (g["level"] == og.level).all() and g["entry_node"] == og.entry_node
+    same_rows = (g["adj0"] == og.adj0).all(1).mean()
+    print("rows identical to the oracle's batch build:", same_rows)
+    assert same_rows == 1.0
+    assert np.array_equal(g["w0"], og.w0)
+    assert (g["adjU"][: og.adjU.shape[0]] == og.adjU).all()
