@@ -413,7 +413,9 @@ __global__ void and_bits_kernel(const uint64_t* a, const uint64_t* b, uint64_t* 
 }
 
 static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list_cap, int* cu_cap, int* hash_bits, size_t* bytes) {
-    int cu = std::min(std::max(ef0 + 4 * s->s0, 2 * ef0), 4096);
+    // closest_up_nodes pops at most k-1 candidates before it has k results when nothing is filtered
+    // (search.rs:205-216), each adding at most one adjacency row of pending candidates.
+    int cu = std::min(std::max(ef0 + k * s->s0, 2 * ef0), 4096);
     int lc = std::max(ef0, cu);
     int slots = next_pow2(std::max(2048, (ef0 * s->s0 * 3) / 2));
     slots = std::max(slots, next_pow2(4 * lc));
