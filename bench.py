@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — k-NN QPS of the nidx_vector HNSW search hot path on B200 (BASELINE.json configs[1]:
+"HNSW search 10M×768 cosine, ef=128 k=10, batch=1024 on 1×B200").
+
+A step = one batch of `--batch` queries through OpenSegment::search (segment.rs:477-567 -> hnsw/search.rs:306-383)
+on one HBM-resident segment.  Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`
+prints ONE JSON line on rank 0.  See DESIGN.md §measurement for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000, help="vectors per segment (per GPU)")
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--ef", type=int, default=128)
+    ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--efc", type=int, default=200)
+    ap.add_argument("--max-batch", type=int, default=8192, help="insertion batch of the GPU HNSW build")
+    ap.add_argument("--latent", type=int, default=16)
+    ap.add_argument("--noise", type=float, default=0.15)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---- synthetic data (BASELINE.md §3 "synthetic embeddings of the named shape") ----------------------
+def gen_vectors(n, d, device, seed, latent, noise, chunk=500_000):
+    """Low-intrinsic-dimension embeddings: gaussian latent -> fixed random linear map + isotropic noise, L2-normalised."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(99)
+    w = torch.randn((latent, d), generator=g, device=device, dtype=torch.float32)
+    g.manual_seed(seed)
+    out = torch.empty((n, d), device=device, dtype=torch.float32)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        z = torch.randn((m, latent), generator=g, device=device, dtype=torch.float32)
+        v = z @ w
+        v += noise * (latent ** 0.5) * torch.randn((m, d), generator=g, device=device, dtype=torch.float32)
+        v /= v.norm(dim=1, keepdim=True)
+        out[i:i + m] = v
+    return out
+
+
+def gen_queries(vecs, nq, seed, distance=0.05):
+    """Queries near data points (segment.rs:880-883)."""
+    import torch
+
+    g = torch.Generator(device=vecs.device)
+    g.manual_seed(seed)
+    idx = torch.randint(0, vecs.shape[0], (nq,), generator=g, device=vecs.device)
+    fuzz = torch.rand((nq, vecs.shape[1]), generator=g, device=vecs.device) * 2 - 1
+    fuzz /= fuzz.norm(dim=1, keepdim=True)
+    q = vecs[idx] + distance * fuzz
+    q /= q.norm(dim=1, keepdim=True)
+    return q.contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def recall_at_k(found, truth):
+    return float(np.mean([len(set(a.tolist()) & set(b.tolist())) / len(b) for a, b in zip(found, truth)]))
+
+
+def export_graph_for_oracle(seg, O, n, m, m0):
+    g = seg.get_graph()
+    og = O.Graph(n, m, m0, g["level"])
+    og.adj0, og.adjU = g["adj0"], g["adjU"]
+    og.entry_node, og.entry_layer = g["entry_node"], g["entry_layer"]
+    return og
+
+
+def cpu_search_rate(O, host_vecs, og, host_q, k, ef, norms, threads, native):
+    t0 = time.perf_counter()
+    ids, sc, cnt, counters = O.hnsw_search(host_vecs, og, host_q, k, ef, nthreads=threads, native=native, norms_=norms)
+    dt = time.perf_counter() - t0
+    return len(host_q) / dt, ids, dt
+
+
+def main():
+    args = parse_args()
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    multi = world > 1 and args.impl == "ours"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from nucliadb_b200 import _lib
+    from nucliadb_b200.segment import VectorSegment, merge_topk
+
+    L = _lib.require_device()
+    n, d, nq, k, ef = args.n, args.dim, args.batch, args.k, args.ef
+    m, m0 = args.m, 2 * args.m
+
+    # ---- setup (untimed): data, segment, GPU HNSW build, ground truth -------------------------------
+    t0 = time.perf_counter()
+    vecs = gen_vectors(n, d, dev, seed=1234567890 + rank, latent=args.latent, noise=args.noise)
+    n_batches = args.steps + args.warmup
+    queries = [gen_queries(vecs, nq, seed=123 + i) for i in range(n_batches)]  # same on every rank for a given i? no: per-rank data
+    if multi:  # every rank must search the SAME queries: take rank 0's
+        for q in queries:
+            dist.broadcast(q, src=0)
+    host_vecs = None
+    if args.impl == "reference" or (rank == 0 and not args.no_cpu_baseline and not multi):
+        host_vecs = vecs.cpu().numpy()
+    seg = VectorSegment.create(vecs, d, similarity=_lib.NIDX_SIM_COSINE, m=m, m0=m0, ef_construction=args.efc, ef_search=ef, device=local_rank)
+    del vecs
+    torch.cuda.empty_cache()
+    t_data = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    seg.build_hnsw(seed=2, max_batch=args.max_batch)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    build_counters = seg.counters()
+
+    # exact ground truth for the first timed batch (the scan kernel, segment.rs:569-623)
+    gt_ids, _, _ = seg.search(queries[args.warmup], k, method=_lib.NIDX_METHOD_BRUTE)
+    torch.cuda.synchronize()
+    gt = gt_ids.cpu().numpy()
+
+    out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+           torch.empty((nq,), dtype=torch.int32, device=dev))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        # The reference's own CPU implementation of the path (oracle port; Rust cannot be built here), all host cores.
+        import oracle as O
+
+        try:
+            O.build(native=True)
+            native = True
+        except Exception:
+            native = False
+        og = export_graph_for_oracle(seg, O, n, m, m0)
+        norms = O.norms(host_vecs, nthreads=cores)
+        sample = min(nq, 256)
+        host_q = [q[:sample].cpu().numpy() for q in queries]
+        for i in range(args.warmup):
+            cpu_search_rate(O, host_vecs, og, host_q[i], k, ef, norms, cores, native)
+        t0 = time.perf_counter()
+        ids0 = None
+        for i in range(args.warmup, n_batches):
+            _, ids, _ = cpu_search_rate(O, host_vecs, og, host_q[i], k, ef, norms, cores, native)
+            if ids0 is None:
+                ids0 = ids
+        dt = time.perf_counter() - t0
+        qps = sample * args.steps / dt
+        line = {"metric": "k-NN QPS @ recall@10", "value": qps, "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "impl": "reference",
+                "config": {"workload": f"HNSW search {n}x{d} cosine, ef={ef} k={k}, batch={nq}", "sample": f"{sample} queries of each batch per step",
+                           "graph": "built by the GPU builder during setup (untimed); the timed region runs only the CPU oracle",
+                           "M": m, "M0": m0, "efC": args.efc},
+                "recall_at_10": recall_at_k(ids0, gt[:sample]),
+                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": f"{sample * args.steps} queries",
+                                 "native_isa": native},
+                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    def step(i):
+        r = seg.search(queries[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=out)
+        if multi:
+            ids_all = [torch.empty_like(out[0]) for _ in range(world)]
+            sc_all = [torch.empty_like(out[1]) for _ in range(world)]
+            dist.all_gather(ids_all, out[0])
+            dist.all_gather(sc_all, out[1])
+            return merge_topk(torch.stack(ids_all), torch.stack(sc_all), device=local_rank)
+        return r
+
+    # ---- warm-up + timed region: inputs resident in HBM (value) --------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
+    launches0 = L.nidx_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` captures exactly the timed region
+        ev0.record()
+        for i in range(args.warmup, n_batches):
+            step(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = L.nidx_launch_count() - launches0
+    if multi:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        dist.barrier()
+    ms_step = ms_total / args.steps
+
+    # ---- recall + roofline accounting (separate, synchronous passes) ----------------------------------
+    ids, _, _ = seg.search(queries[args.warmup], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+    torch.cuda.synchronize()
+    ids_np = ids.cpu().numpy()
+    recall = recall_at_k(ids_np, gt)
+    kernel_ms, alg_bytes = [], []
+    ld = (d + 3) // 4 * 4
+    for i in range(args.warmup, min(n_batches, args.warmup + 8)):
+        seg.search(queries[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=out)
+        kernel_ms.append(seg.last_kernel_ms())
+        c = seg.counters()
+        alg_bytes.append(c["similarities"] * (ld * 4 + 4) + c["expansions"] * (2 * m) * 4)
+        overflow = c["overflows"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = float(np.mean(alg_bytes)) / (float(np.mean(kernel_ms)) * 1e-3) / 1e9
+
+    # ---- e2e: the same metric through the host-buffer C ABI call (H2D + D2H inside the timed region) --
+    hq = [torch.empty((nq, d), dtype=torch.float32).pin_memory() for _ in range(n_batches)]
+    for h, q in zip(hq, queries):
+        h.copy_(q)
+    torch.cuda.synchronize()
+    hq_np = [h.numpy() for h in hq]
+    for i in range(args.warmup):
+        seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_batches):
+        e_ids, e_sc, e_cnt = seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    if multi:
+        t = torch.tensor([e2e_dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_qps = world * nq * args.steps / e2e_dt
+
+    # ---- CPU baseline (rank 0, N=1): the oracle on the host cores, bounded sample ---------------------
+    cpu = None
+    if rank == 0 and host_vecs is not None:
+        import oracle as O
+
+        try:
+            O.build(native=True)
+            native = True
+        except Exception:
+            native = False
+        og = export_graph_for_oracle(seg, O, n, m, m0)
+        norms = O.norms(host_vecs, nthreads=cores)
+        hq0 = queries[args.warmup].cpu().numpy()
+        rate, _, _ = cpu_search_rate(O, host_vecs, og, hq0[:64], k, ef, norms, cores, native)
+        ns = int(max(64, min(len(hq0), rate * args.cpu_seconds)))
+        rate, cids, dt = cpu_search_rate(O, host_vecs, og, hq0[:ns], k, ef, norms, cores, native)
+        same = float(np.mean(cids == ids_np[:ns].astype(np.uint32)))
+        cpu = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "sample": f"{ns} queries of the first timed batch, {dt:.1f} s",
+               "native_isa": native, "ids_identical_to_gpu": same}
+
+    if rank == 0:
+        qps_units = world * nq * args.steps / (ms_total * 1e-3)
+        line = {
+            "metric": "k-NN QPS @ recall@10", "value": qps_units, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"HNSW search {n}x{d} cosine, ef={ef} k={k}, batch={nq}", "segments": world, "vectors_per_segment": n,
+                       "M": m, "M0": m0, "efC": args.efc, "l2": "inputs larger than L2 (30.7 GB of vectors per GPU, fresh queries every step)",
+                       "unit_note": "one unit = one query searched on one segment; merged_qps = user-visible queries/s over all segments",
+                       "data_gen": f"latent={args.latent} noise={args.noise} normalised; queries = data point + 0.05 * unit noise"},
+            "merged_qps": nq * args.steps / (ms_total * 1e-3),
+            "recall_at_10": recall,
+            "build": {"seconds": t_build, "vectors_per_s": n / t_build, "similarities": build_counters["similarities"], "max_batch": args.max_batch,
+                      "data_seconds": t_data},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "hnsw_search_kernel", "kernel_ms": float(np.mean(kernel_ms)), "alg_bytes_per_launch": float(np.mean(alg_bytes)),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4},
+            "gpu_launches": int(launches),
+            "visited_overflows": int(overflow),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if multi:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

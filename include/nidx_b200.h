@@ -135,6 +135,11 @@ int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, in
  * SURVEY 8d): [0] similarity evaluations, [1] node expansions, [2] visited-set overflows. */
 int nidx_vec_counters(nidx_vec_segment* seg, uint64_t out[3]);
 
+/* Device time (CUDA events on the caller's stream) of the dominant kernel of the last nidx_vec_search on
+ * this segment: hnsw_search_kernel, or the first scan_scores_kernel of a brute-force call.  Diagnostics
+ * for the roofline line of bench.py; not meaningful under concurrent searches. */
+int nidx_vec_last_kernel_ms(nidx_vec_segment* seg, float* ms);
+
 /* ------------------------------------------------------------------------------------------
  * Text segment: BM25 over device-resident postings
  * (reference: tantivy TopDocs::order_by_score called at nidx_text/src/reader.rs:433-435 and

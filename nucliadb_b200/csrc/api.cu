@@ -133,6 +133,7 @@ struct nidx_vec_segment {
     uint32_t* d_adjU = nullptr; float* d_wU = nullptr;
     unsigned long long* d_counters = nullptr;  // [4]
     unsigned int* d_work_counter = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the dominant kernel of the last search (bench roofline)
     WorkspacePool pool;
 
     VecDev vdev() const {
@@ -255,6 +256,8 @@ static int finish_create(nidx_vec_segment* s, const uint32_t* paragraph_of_host)
     CU(cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
     CU(cudaMemset(s->d_counters, 0, 4 * sizeof(unsigned long long)));
     CU(cudaMalloc(&s->d_work_counter, 64));
+    CU(cudaEventCreate(&s->ev_k0));
+    CU(cudaEventCreate(&s->ev_k1));
     CU(cudaDeviceSynchronize());
     return 0;
 }
@@ -321,6 +324,8 @@ void nidx_vec_close(nidx_vec_segment* s) {
     free_graph(s);
     cudaFree(s->d_vecs); cudaFree(s->d_norms); cudaFree(s->d_par_of); cudaFree(s->d_par_first); cudaFree(s->d_alive);
     cudaFree(s->d_counters); cudaFree(s->d_work_counter);
+    if (s->ev_k0) cudaEventDestroy(s->ev_k0);
+    if (s->ev_k1) cudaEventDestroy(s->ev_k1);
     delete s;
 }
 
@@ -388,6 +393,14 @@ int nidx_vec_counters(nidx_vec_segment* s, uint64_t out[3]) {
     unsigned long long h[4];
     CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2] + h[3];
+    return 0;
+}
+
+int nidx_vec_last_kernel_ms(nidx_vec_segment* s, float* ms) {
+    if (!s || !ms) return fail(NIDX_EINVAL, "null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaEventSynchronize(s->ev_k1));
+    CU(cudaEventElapsedTime(ms, s->ev_k0, s->ev_k1));
     return 0;
 }
 
@@ -530,8 +543,10 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
             uint64_t n_vchunks = (s->n + SCAN_WARPS * SCAN_VPW - 1) / (SCAN_WARPS * SCAN_VPW);
             uint64_t grid = n_vchunks * n_qtiles;
             if (grid > 0x7FFFFFFFull) return fail(NIDX_EINVAL, "scan grid too large");
+            if (q0 == 0) CU(cudaEventRecord(s->ev_k0, stream));
             scan_scores_kernel<<<(unsigned)grid, SCAN_WARPS * 32, smem_scan, stream>>>(V, dq + (size_t)q0 * s->ld, w.qnorms.as<float>() + q0, nqg, n_qtiles,
                                                                                      w.scores.as<float>());
+            if (q0 == 0) CU(cudaEventRecord(s->ev_k1, stream));
             LAUNCHED();
             scan_select_kernel<<<dim3(n_chunks, nqg), 256, (size_t)cap * 8, stream>>>(w.scores.as<float>(), (uint32_t)s->n, s->n_par, s->d_par_first, nullptr, bits,
                                                                                       p->min_score, k, cap, n_chunks, w.partial.as<uint64_t>());
@@ -564,7 +579,9 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hnsw_search_kernel, HS_THREADS, smem));
         int grid = std::min(nq, std::max(1, occ) * s->sm_count);
+        CU(cudaEventRecord(s->ev_k0, stream));
         hnsw_search_kernel<<<grid, HS_THREADS, smem, stream>>>(V, s->gdev(), a);
+        CU(cudaEventRecord(s->ev_k1, stream));
         LAUNCHED();
         CU(cudaGetLastError());
     }

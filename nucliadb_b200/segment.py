@@ -142,6 +142,11 @@ class VectorSegment:
                                 None))
         return ids, scores, counts
 
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(_lib.load().nidx_vec_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def counters(self):
         out = (C.c_uint64 * 3)()
         check(_lib.load().nidx_vec_counters(self._h, out))

@@ -15,6 +15,13 @@
 
 using namespace nidx_oracle;
 
+// One visited-set scratch per OS thread, kept across calls: the reference's FxHashSet costs nothing to
+// set up, so the epoch array must not be re-allocated (O(n) page faults) on every batch.
+static Scratch& tls_scratch() {
+    static thread_local Scratch sc;
+    return sc;
+}
+
 static Data make_data(const float* vecs, const float* norms, uint32_t n, int d, int ld, int sim) {
     Data D;
     D.vecs = vecs; D.norms = norms; D.n = n; D.d = d; D.ld = ld; D.sim = sim;
@@ -77,7 +84,6 @@ void oracle_hnsw_search(const float* vecs, const float* norms, uint32_t n, int d
     GraphView G = make_view(n, M, M0, level, entry_node, entry_layer, const_cast<uint32_t*>(adj0), nullptr, upper_off,
                             const_cast<uint32_t*>(adjU), nullptr);
     int nt = nthreads > 0 ? nthreads : 1;
-    std::vector<Scratch> scratch(nt);
     std::vector<Counters> cnts(nt);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
     for (int qi = 0; qi < nq; ++qi) {
@@ -88,7 +94,7 @@ void oracle_hnsw_search(const float* vecs, const float* norms, uint32_t n, int d
         Query q{queries + (size_t)qi * qld, sim == SIM_COSINE ? norm_ordered(queries + (size_t)qi * qld, d) : 0.0f};
         NodeFilter f;
         f.filter_bits = filter_bits; f.paragraph_of = paragraph_of; f.with_duplicates = with_duplicates != 0; f.multi_vector = multi_vector != 0;
-        auto r = hnsw_search(D, G, q, (size_t)k, ef, min_score, f, scratch[t], &cnts[t]);
+        auto r = hnsw_search(D, G, q, (size_t)k, ef, min_score, f, tls_scratch(), &cnts[t]);
         if (r.size() > (size_t)k) r.resize(k);  // segment.rs:555 .take(top_k)
         out_count[qi] = (int)r.size();
         for (int j = 0; j < k; ++j) {
@@ -149,7 +155,6 @@ double oracle_hnsw_build(const float* vecs, const float* norms, uint32_t n, int 
     GraphView G = make_view(n, M, M0, level, entry_node, entry_layer, adj0, w0, upper_off, adjU, wU);
     auto t0 = std::chrono::steady_clock::now();
     int nt = nthreads > 0 ? nthreads : 1;
-    std::vector<Scratch> scratch(nt);
     std::vector<Counters> cnts(nt);
     uint32_t begin = 0;
     for (uint32_t b = 0; b < n_batches; ++b) {
@@ -161,7 +166,7 @@ double oracle_hnsw_build(const float* vecs, const float* norms, uint32_t n, int 
 #ifdef _OPENMP
             t = omp_get_thread_num();
 #endif
-            found[i - begin] = insert_search(D, G, prm, order[i], scratch[t], &cnts[t]);
+            found[i - begin] = insert_search(D, G, prm, order[i], tls_scratch(), &cnts[t]);
         }
         std::vector<uint32_t> idx(end - begin);
         for (uint32_t i = 0; i < end - begin; ++i) idx[i] = i;
