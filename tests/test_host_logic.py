@@ -1,0 +1,68 @@
+"""Host-side logic of the reference-interface mirror (no GPU): field keys, label filters, Fssc, BM25
+host helpers, use of the oracle only as the checker."""
+import uuid
+
+import numpy as np
+
+import oracle as O
+from nucliadb_b200 import text as T
+from nucliadb_b200 import vector as V
+
+
+def _segment(keys, labels):
+    cfg = V.VectorConfig(dimension=4)
+    return V.OpenSegment(cfg, None, keys, labels, [None] * len(keys), list(range(len(keys) + 1)))
+
+
+RID = "9cb39c75f8d9498d8f82d92b173011f5"
+
+
+def test_field_key_matches_reference_layout():  # utils.rs:80-117
+    fk = V.field_key(f"{RID}/f/file/0-100")
+    assert fk == uuid.UUID(RID).bytes + b"f/file"
+    assert V.field_key(RID) == uuid.UUID(RID).bytes
+    assert V.field_key(f"{RID}/f") is None and V.field_key("not-a-uuid/f/x") is None
+
+
+def test_label_filter_prefix_at_segment_boundary():  # inverted_index/paragraph.rs:64-66, segment/tests.rs:343-381
+    seg = _segment([f"{RID}/f/a/0-1", f"{RID}/f/a/1-2", f"{RID}/f/b/0-1"], [["/l/labelset/LABEL"], ["/l/labelset/LABEL_0"], ["/l/other/x"]])
+    assert seg._clause(V.Literal("/l/labelset")).tolist() == [True, True, False]
+    assert seg._clause(V.Literal("/l/labelset/LABEL")).tolist() == [True, False, False]
+    assert seg._clause(V.Not(V.Literal("/l/labelset"))).tolist() == [False, False, True]
+    both = V.Operation("or", (V.Literal("/l/labelset/LABEL_0"), V.Literal("/l/other")))
+    assert seg._clause(both).tolist() == [False, True, True]
+    assert seg.filter_bitset([V.Literal("/l/labelset"), V.Literal("/l/other")], operator_and=True).tolist() == [False, False, False]
+    assert seg.filter_bitset([V.Literal("/l/labelset"), V.Literal("/l/other")], operator_and=False).tolist() == [True, True, True]
+
+
+def test_key_prefix_set_is_an_exact_field_lookup():  # paragraph.rs:150-155 uses field_index.get (exact)
+    other = "00000000000000000000000000000001"
+    seg = _segment([f"{RID}/f/a/0-1", f"{RID}/f/b/0-1", f"{other}/f/a/0-1"], [[], [], []])
+    assert seg._clause(V._KeyPrefixSet(frozenset([f"{RID}/f/a"]))).tolist() == [True, False, False]
+    assert seg._clause(V._KeyPrefixSet(frozenset([RID]))).tolist() == [False, False, False]
+
+
+def test_fssc_matches_oracle_restatement():
+    rng = np.random.default_rng(0)
+    for with_dups in (True, False):
+        mine, theirs = V._Fssc(5, with_dups), O.Fssc(5, with_dups)
+        for i in range(60):
+            pid = f"p{rng.integers(0, 20)}"
+            score = float(np.float32(rng.random()))
+            vb = bytes([int(rng.integers(0, 12))])
+            mine.add(pid, score, i, vb)
+            theirs.add(pid, score, 0, i, vb)
+        seg, addr, sc = theirs.result()
+        got = mine.result()
+        assert [p for _, _, p in got] == list(addr)
+        assert np.allclose([s for s, _, _ in got], sc)
+
+
+def test_fieldnorm_code_matches_oracle_table():
+    for n in list(range(0, 3000)) + [10_000, 65_535, 1_000_000, 2_013_265_944]:
+        assert T.fieldnorm_to_id(n) == O.fieldnorm_to_id(n), n
+
+
+def test_tokenizer_is_lowercase_alnum():
+    assert T.tokenize("Hello, World! it's 42") == ["hello", "world", "it", "s", "42"]
+    assert T.tokenize("x" * 41) == []
