@@ -29,7 +29,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="vectors per segment (per GPU)")
+    ap.add_argument("--vectors", dest="n", type=int, default=10_000_000, help="vectors per segment (per GPU)")
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
@@ -289,11 +289,15 @@ def main():
     hq_np = [h.numpy() for h in hq]
     for i in range(args.warmup):
         seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+    e2e_steps = []
     t0 = time.perf_counter()
     for i in range(args.warmup, n_batches):
+        t1 = time.perf_counter()
         e_ids, e_sc, e_cnt = seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+        e2e_steps.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
+    print(f"[bench] e2e per-step ms: min {min(e2e_steps) * 1e3:.3f} median {np.median(e2e_steps) * 1e3:.3f} max {max(e2e_steps) * 1e3:.3f}", file=sys.stderr)
     if multi:
         t = torch.tensor([e2e_dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

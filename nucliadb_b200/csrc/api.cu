@@ -425,6 +425,22 @@ __global__ void and_bits_kernel(const uint64_t* a, const uint64_t* b, uint64_t* 
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
 }
 
+// hnsw_search_kernel is instantiated for the common row lengths (ld = NG * 128 floats); other dimensions use
+// the run-time loop (NG = 0).
+typedef void (*hs_kernel_t)(VecDev, GraphDev, SearchArgs);
+static hs_kernel_t pick_search_kernel(int ld) {
+    if (ld % 128 == 0) switch (ld / 128) {
+        case 1: return hnsw_search_kernel<1>;
+        case 2: return hnsw_search_kernel<2>;
+        case 3: return hnsw_search_kernel<3>;
+        case 4: return hnsw_search_kernel<4>;
+        case 6: return hnsw_search_kernel<6>;
+        case 8: return hnsw_search_kernel<8>;
+        default: break;
+    }
+    return hnsw_search_kernel<0>;
+}
+
 static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list_cap, int* cu_cap, int* hash_bits, size_t* bytes) {
     // closest_up_nodes pops at most k-1 candidates before it has k results when nothing is filtered
     // (search.rs:205-216), each adding at most one adjacency row of pending candidates.
@@ -575,12 +591,13 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
         a.counters = s->d_counters;
         CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
         CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
-        CU(cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hs_kernel_t kern = pick_search_kernel(s->ld);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hnsw_search_kernel, HS_THREADS, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HS_THREADS, smem));
         int grid = std::min(nq, std::max(1, occ) * s->sm_count);
         CU(cudaEventRecord(s->ev_k0, stream));
-        hnsw_search_kernel<<<grid, HS_THREADS, smem, stream>>>(V, s->gdev(), a);
+        kern<<<grid, HS_THREADS, smem, stream>>>(V, s->gdev(), a);
         CU(cudaEventRecord(s->ev_k1, stream));
         LAUNCHED();
         CU(cudaGetLastError());
@@ -717,9 +734,10 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
         hash_bits = ilog2(slots);
         size_t smem_search = hs_smem_bytes(s->ld, list_cap, hash_bits);
         if (smem_search > 200 * 1024) return fail(NIDX_EINVAL, "HNSW build search needs %zu bytes of shared memory", smem_search);
-        CU(cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search));
+        hs_kernel_t kern = pick_search_kernel(s->ld);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_search));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hnsw_search_kernel, HS_THREADS, smem_search));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HS_THREADS, smem_search));
         size_t row_bytes = (size_t)s->ld * 4;
         size_t budget = 96 * 1024;
         int cache_sel = (int)std::min<size_t>(M, budget / row_bytes);
@@ -744,7 +762,7 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
             a.hash_bits = hash_bits; a.list_cap = list_cap; a.cu_cap = 0; a.work_counter = s->d_work_counter; a.counters = s->d_counters;
             CU(cudaMemsetAsync(s->d_work_counter, 0, 4, stream));
             int grid = std::min(nb, std::max(1, occ) * s->sm_count);
-            hnsw_search_kernel<<<grid, HS_THREADS, smem_search, stream>>>(V, G, a);
+            kern<<<grid, HS_THREADS, smem_search, stream>>>(V, G, a);
             LAUNCHED();
             BuildArgs ba;
             ba.n_work = nw; ba.w_pos = d_wpos + wstart[begin]; ba.w_layer = d_wlayer + wstart[begin]; ba.order = d_order; ba.batch_begin = begin;

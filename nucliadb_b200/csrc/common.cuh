@@ -96,6 +96,37 @@ __device__ __forceinline__ float warp_dot(const float4* __restrict__ a, const fl
     return butterfly_sum(__fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw)));
 }
 
+// Same arithmetic, compile-time row length: NG float4 groups per lane (ld == NG * 128 floats).  No
+// predication, immediate load offsets; NG == 0 falls back to the run-time loop above.
+template <int NG>
+__device__ __forceinline__ float warp_dot_t(const float4* __restrict__ a, const float4* __restrict__ b, int ngroups, int lane) {
+    if constexpr (NG == 0) {
+        return warp_dot(a, b, ngroups, lane);
+    } else {
+        float4 va[NG];
+#pragma unroll
+        for (int j = 0; j < NG; ++j) va[j] = ldg_stream(a + j * 32 + lane);
+        float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            float4 vb = b[j * 32 + lane];
+            ax = __fmaf_rn(va[j].x, vb.x, ax);
+            ay = __fmaf_rn(va[j].y, vb.y, ay);
+            az = __fmaf_rn(va[j].z, vb.z, az);
+            aw = __fmaf_rn(va[j].w, vb.w, aw);
+        }
+        return butterfly_sum(__fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw)));
+    }
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
+}
+
 // dense_f32.rs:29-33 with simsimd's edge cases; na, nb = precomputed ordered norms.
 __device__ __forceinline__ float cosine_from_parts(float ab, float na, float nb) {
     if (na == 0.0f && nb == 0.0f) return 1.0f;

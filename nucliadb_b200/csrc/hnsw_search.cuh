@@ -60,7 +60,10 @@ struct SearchCtx {
     uint32_t* hash;
     uint32_t* todo_id;
     uint64_t* todo_key;
+    uint32_t* pref_row;   // [2][HS_MAX_ROW] speculatively prefetched adjacency rows (double buffered by hop parity)
+    uint32_t* pref_node;  // [2] node each buffer belongs to (NIL = none)
     int *s_len, *s_best, *s_best_next, *s_ntodo, *s_hash_count, *s_flag, *s_nadmit;
+    unsigned hop;
     uint32_t hash_mask;
     int hash_bits, hash_limit;
     float qnorm;
@@ -68,7 +71,7 @@ struct SearchCtx {
 };
 
 __host__ __device__ __forceinline__ size_t hs_smem_bytes(int ld, int list_cap, int hash_bits) {
-    return (size_t)ld * 4 + (size_t)list_cap * 16 + ((size_t)4 << hash_bits) + HS_MAX_ROW * 12 + 64;
+    return (size_t)ld * 4 + (size_t)list_cap * 16 + ((size_t)4 << hash_bits) + HS_MAX_ROW * 12 + HS_MAX_ROW * 8 + 16 + 64;
 }
 
 // returns true iff y was not in the set (and is now).  A full table reports "already visited".
@@ -87,7 +90,7 @@ __device__ __forceinline__ bool hash_insert(SearchCtx& c, uint32_t y, bool& over
 __device__ inline void hs_reseed(SearchCtx& c) {
     __syncthreads();
     for (int i = threadIdx.x; i <= (int)c.hash_mask; i += blockDim.x) c.hash[i] = NIL;
-    if (threadIdx.x == 0) { *c.s_hash_count = 0; *c.s_best = 0; }
+    if (threadIdx.x == 0) { *c.s_hash_count = 0; *c.s_best = 0; c.pref_node[0] = NIL; c.pref_node[1] = NIL; }
     __syncthreads();
     int len = *c.s_len;
     bool ov = false;
@@ -102,18 +105,25 @@ __device__ inline void hs_reseed(SearchCtx& c) {
 }
 
 // Expand `node` (already chosen): gather unvisited neighbours (warp 0), score them (all warps).
-// admit_full_list: layer_search admission (search.rs:286) -- when the list holds `ef` entries only keys
-// better than the worst survive; closest_up_nodes admission (search.rs:231) is score >= min_score.
-template <bool CU>
-__device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& c, uint32_t node, int layer, int ef, float min_score) {
+// Admission: layer_search (search.rs:286) -- when the list holds `ef` entries only keys better than the
+// worst survive; closest_up_nodes (search.rs:231) -- score >= min_score.
+// Speculation: while warp 0 works, the last warp starts an asynchronous copy (cp.async) of the adjacency
+// row of the node that will be expanded next if no new neighbour outranks it -- `pred_idx` in the list --
+// into the other half of a double buffer; the row's HBM latency then overlaps this expansion's vector loads.
+template <bool CU, int NG>
+__device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& c, uint32_t node, int layer, int ef, float min_score, int best) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int stride = G.stride(layer);
+    unsigned cur = c.hop & 1u;
     if (warp == 0) {
+        const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
+        bool hit = c.pref_node[cur] == node;
         const uint32_t* row = G.row(node, layer);
-        int stride = G.stride(layer);
         int ntodo = 0;
         bool ov = false;
         for (int e0 = 0; e0 < stride; e0 += 32) {
-            uint32_t y = (e0 + lane < stride) ? __ldg(row + e0 + lane) : NIL;
+            uint32_t y = NIL;
+            if (e0 + lane < stride) y = hit ? prow[e0 + lane] : __ldg(row + e0 + lane);
             bool fresh = (y != NIL) && hash_insert(c, y, ov);
             unsigned mask = __ballot_sync(0xFFFFFFFFu, fresh);
             if (fresh) c.todo_id[ntodo + __popc(mask & ((1u << lane) - 1))] = y;
@@ -127,6 +137,26 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
             *c.s_nadmit = 0;
             c.n_expand++;
         }
+    } else if (warp == HS_WARPS - 1) {
+        int len = *c.s_len;
+        int pred = -1;
+        if (CU) {
+            pred = len > 1 ? 1 : -1;
+        } else {
+            for (int i0 = best + 1; i0 < len && pred < 0; i0 += 32) {
+                int i = i0 + lane;
+                unsigned m = __ballot_sync(0xFFFFFFFFu, i < len && (c.A[i] & 1ull));
+                if (m) pred = i0 + __ffs(m) - 1;
+            }
+        }
+        uint32_t pnode = NIL;
+        if (pred >= 0) {
+            pnode = key_id(c.A[pred]);
+            const uint32_t* row2 = G.row(pnode, layer);
+            uint32_t* dst = c.pref_row + (cur ^ 1u) * HS_MAX_ROW;
+            for (int e = lane; e < stride; e += 32) cp_async4(dst + e, row2 + e);
+        }
+        if (lane == 0) c.pref_node[cur ^ 1u] = pnode;
     }
     __syncthreads();
     int ntodo = *c.s_ntodo, len = *c.s_len;
@@ -134,9 +164,10 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
     int ng = V.ld >> 2;
     for (int j = warp; j < ntodo; j += HS_WARPS) {
         uint32_t y = c.todo_id[j];
-        float ab = warp_dot(reinterpret_cast<const float4*>(V.vecs + (size_t)y * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
+        float vnorm = V.sim == SIM_COSINE ? __ldg(V.norms + y) : 0.0f;
+        float ab = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)y * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
         if (lane == 0) {
-            float s = finish_similarity(V, ab, y, c.qnorm);
+            float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, vnorm, c.qnorm) : ab;
             uint64_t key = make_key(s, y, 1);
             bool admit = CU ? (s >= min_score) : (key > wkey);
             c.todo_key[j] = admit ? key : 0;
@@ -144,13 +175,15 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
             c.n_dist++;
         }
     }
+    if (warp == HS_WARPS - 1) cp_async_commit_wait_all();
+    c.hop++;
     __syncthreads();
 }
 
 // Merge the admitted todo keys into the sorted list A -> B (rank merge, no sort), keep at most `cap`.
 // CU: entry 0 (the popped candidate) is dropped.  Afterwards A/B are swapped and s_len/s_best updated.
 template <bool CU>
-__device__ inline void hs_merge(SearchCtx& c, int cap) {
+__device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
     int len = *c.s_len, ntodo = *c.s_ntodo;
     int first = CU ? 1 : 0;
     for (int t = threadIdx.x; t < len - first + ntodo; t += blockDim.x) {
@@ -159,6 +192,7 @@ __device__ inline void hs_merge(SearchCtx& c, int cap) {
         if (t < len - first) {
             int i = t + first;
             key = c.A[i];
+            if (!CU && i == best) key &= ~1ull;  // the entry just expanded
             int shift = 0;
             for (int j = 0; j < ntodo; ++j) shift += (c.todo_key[j] > key);
             p = t + shift;
@@ -192,15 +226,14 @@ __device__ inline void hs_merge(SearchCtx& c, int cap) {
 }
 
 // hnsw/search.rs:242-304 on the list held in shared memory.
+template <int NG>
 __device__ inline void hs_layer_search(const VecDev& V, const GraphDev& G, SearchCtx& c, int layer, int ef) {
     while (true) {
         int best = *c.s_best, len = *c.s_len;
         if (best >= len) break;
         uint64_t ckey = c.A[best];
-        __syncthreads();
-        if (threadIdx.x == 0) c.A[best] = ckey & ~1ull;
-        hs_expand<false>(V, G, c, key_id(ckey), layer, ef, 0.0f);
-        hs_merge<false>(c, ef);
+        hs_expand<false, NG>(V, G, c, key_id(ckey), layer, ef, 0.0f, best);
+        hs_merge<false>(c, ef, best);
     }
 }
 
@@ -233,6 +266,7 @@ __device__ inline bool hs_passes(const VecDev& V, const SearchArgs& a, uint32_t 
 }
 
 // hnsw/search.rs:188-240.  Results go straight to out_ids/out_scores (already descending).
+template <int NG>
 __device__ inline int hs_closest_up(const VecDev& V, const GraphDev& G, SearchCtx& c, const SearchArgs& a, uint32_t* out_ids, float* out_scores) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     hs_reseed(c);
@@ -255,12 +289,13 @@ __device__ inline int hs_closest_up(const VecDev& V, const GraphDev& G, SearchCt
         __syncthreads();
         nacc += *c.s_flag;
         if (nacc == a.k) break;  // 214
-        hs_expand<true>(V, G, c, node, 0, 0, a.min_score);
-        hs_merge<true>(c, a.cu_cap);
+        hs_expand<true, NG>(V, G, c, node, 0, 0, a.min_score, 0);
+        hs_merge<true>(c, a.cu_cap, 0);
     }
     return nacc;
 }
 
+template <int NG>
 __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, GraphDev G, SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ints[8];
@@ -272,7 +307,10 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
     c.B = reinterpret_cast<uint64_t*>(p); p += (size_t)a.list_cap * 8;
     c.todo_key = reinterpret_cast<uint64_t*>(p); p += HS_MAX_ROW * 8;
     c.hash = reinterpret_cast<uint32_t*>(p); p += (size_t)4 << a.hash_bits;
-    c.todo_id = reinterpret_cast<uint32_t*>(p);
+    c.todo_id = reinterpret_cast<uint32_t*>(p); p += HS_MAX_ROW * 4;
+    c.pref_row = reinterpret_cast<uint32_t*>(p); p += 2 * HS_MAX_ROW * 4;
+    c.pref_node = reinterpret_cast<uint32_t*>(p);
+    c.hop = 0;
     c.s_len = &s_ints[0]; c.s_best = &s_ints[1]; c.s_best_next = &s_ints[2]; c.s_ntodo = &s_ints[3];
     c.s_hash_count = &s_ints[4]; c.s_flag = &s_ints[5]; c.s_nadmit = &s_ints[6];
     c.hash_bits = a.hash_bits;
@@ -299,7 +337,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
         // entry point: similarity + single-entry list (search.rs:256-261)
         if (threadIdx.x < 32) {
             uint32_t ep = G.entry_node;
-            float ab = warp_dot(reinterpret_cast<const float4*>(V.vecs + (size_t)ep * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
+            float ab = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)ep * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
             if (lane == 0) {
                 c.A[0] = make_key(finish_similarity(V, ab, ep, c.qnorm), ep, 1);
                 *c.s_len = 1;
@@ -314,7 +352,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
             if (a.mode == 0) ef = layer == 0 ? a.ef0 : 1;
             else ef = layer <= top ? a.efC : 1;
             hs_reseed(c);
-            hs_layer_search(V, G, c, layer, ef);
+            hs_layer_search<NG>(V, G, c, layer, ef);
             __syncthreads();
             if (a.mode == 1 && layer <= top && layer < HS_MAX_LAYERS) {
                 int len = *c.s_len;
@@ -332,7 +370,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
         if (a.mode == 0) {
             uint32_t* oi = a.out_ids + (size_t)q * a.k;
             float* os = a.out_scores + (size_t)q * a.k;
-            int nacc = hs_closest_up(V, G, c, a, oi, os);
+            int nacc = hs_closest_up<NG>(V, G, c, a, oi, os);
             __syncthreads();
             // search.rs:381 `filtered_result.sort_by(|a, b| b.1.total_cmp(&a.1))`: stable, descending.
             // (closest_up_nodes can accept a late-found neighbour that outranks earlier results.)
