@@ -441,6 +441,20 @@ static hs_kernel_t pick_search_kernel(int ld) {
     return hnsw_search_kernel<0>;
 }
 
+typedef void (*scan_kernel_t)(VecDev, const float*, const float*, int, int, float*);
+static scan_kernel_t pick_scan_kernel(int ld) {
+    if (ld % 128 == 0) switch (ld / 128) {
+        case 1: return scan_scores_kernel_t<1, 4>;
+        case 2: return scan_scores_kernel_t<2, 4>;
+        case 3: return scan_scores_kernel_t<3, 4>;
+        case 4: return scan_scores_kernel_t<4, 2>;
+        case 6: return scan_scores_kernel_t<6, 2>;
+        case 8: return scan_scores_kernel_t<8, 2>;
+        default: break;
+    }
+    return scan_scores_kernel;
+}
+
 static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list_cap, int* cu_cap, int* hash_bits, size_t* bytes) {
     // closest_up_nodes pops at most k-1 candidates before it has k results when nothing is filtered
     // (search.rs:205-216), each adding at most one adjacency row of pending candidates.
@@ -548,7 +562,8 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
         ENSURE(w.scores, (size_t)qgroup * s->n * 4);
         ENSURE(w.partial, (size_t)qgroup * n_chunks * k * 8);
         size_t smem_scan = (size_t)SCAN_QT * s->ld * 4;
-        if (smem_scan > 48 * 1024) CU(cudaFuncSetAttribute(scan_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+        scan_kernel_t scan_kern = pick_scan_kernel(s->ld);
+        if (smem_scan > 48 * 1024) CU(cudaFuncSetAttribute(scan_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         if ((size_t)cap * 8 > 48 * 1024) {
             CU(cudaFuncSetAttribute(scan_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
             CU(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
@@ -560,7 +575,7 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
             uint64_t grid = n_vchunks * n_qtiles;
             if (grid > 0x7FFFFFFFull) return fail(NIDX_EINVAL, "scan grid too large");
             if (q0 == 0) CU(cudaEventRecord(s->ev_k0, stream));
-            scan_scores_kernel<<<(unsigned)grid, SCAN_WARPS * 32, smem_scan, stream>>>(V, dq + (size_t)q0 * s->ld, w.qnorms.as<float>() + q0, nqg, n_qtiles,
+            scan_kern<<<(unsigned)grid, SCAN_WARPS * 32, smem_scan, stream>>>(V, dq + (size_t)q0 * s->ld, w.qnorms.as<float>() + q0, nqg, n_qtiles,
                                                                                      w.scores.as<float>());
             if (q0 == 0) CU(cudaEventRecord(s->ev_k1, stream));
             LAUNCHED();
@@ -727,7 +742,7 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
         CU(cudaMalloc(&d_cub, cub_bytes));
 
         // shared-memory plans
-        int ef0 = efC;
+
         int list_cap = efC, hash_bits;
         int slots = next_pow2(std::max(2048, (efC * s->s0 * 3) / 2));
         slots = std::max(slots, next_pow2(4 * list_cap));
@@ -747,7 +762,7 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
         CU(cudaFuncSetAttribute(select_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
         CU(cudaFuncSetAttribute(reverse_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rev));
         CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
-        (void)ef0;
+
 
         VecDev V = s->vdev();
         GraphDev G = s->gdev();
@@ -871,7 +886,10 @@ struct nidx_txt_segment {
     uint64_t n_post = 0;
     uint64_t* d_term_off = nullptr;
     uint32_t* d_doc = nullptr;
-    uint32_t* d_tf = nullptr;
+    uint32_t* d_tfn = nullptr;        // tf << 8 | fieldnorm id
+    uint32_t* d_skip_row = nullptr;   // [n_terms]
+    uint32_t* d_skip = nullptr;       // [rows][n_tiles + 1]
+    uint32_t n_tiles = 0;
     unsigned char* d_fieldnorm = nullptr;
     uint64_t* d_alive = nullptr;
     float* d_weight = nullptr;   // [n_terms]
@@ -917,18 +935,46 @@ int nidx_txt_create(int32_t device, uint32_t n_docs, uint32_t n_terms, const uin
     cudaGetDeviceProperties(&prop, device);
     t->sm_count = prop.multiProcessorCount;
     r = [&]() -> int {
+        t->n_tiles = (n_docs + BM_TILE - 1) / BM_TILE;
         CU(cudaMalloc(&t->d_term_off, ((size_t)n_terms + 1) * 8));
         CU(cudaMalloc(&t->d_doc, std::max<uint64_t>(t->n_post, 1) * 4));
-        CU(cudaMalloc(&t->d_tf, std::max<uint64_t>(t->n_post, 1) * 4));
+        CU(cudaMalloc(&t->d_tfn, std::max<uint64_t>(t->n_post, 1) * 4));
         CU(cudaMalloc(&t->d_fieldnorm, std::max<uint32_t>(n_docs, 1)));
         CU(cudaMalloc(&t->d_weight, std::max<uint32_t>(n_terms, 1) * 4));
         CU(cudaMalloc(&t->d_norm_cache, 1024));
+        CU(cudaMalloc(&t->d_skip_row, std::max<uint32_t>(n_terms, 1) * 4));
         CU(cudaMemcpy(t->d_term_off, term_off, ((size_t)n_terms + 1) * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(t->d_fieldnorm, fieldnorm_id, n_docs, cudaMemcpyHostToDevice));
         if (t->n_post) {
             CU(cudaMemcpy(t->d_doc, post_doc, t->n_post * 4, cudaMemcpyHostToDevice));
-            if (post_tf) CU(cudaMemcpy(t->d_tf, post_tf, t->n_post * 4, cudaMemcpyHostToDevice));
+            uint32_t* d_tf = nullptr;   // staged only to be packed with the fieldnorm code
+            if (post_tf) {
+                CU(cudaMalloc(&d_tf, t->n_post * 4));
+                CU(cudaMemcpy(d_tf, post_tf, t->n_post * 4, cudaMemcpyHostToDevice));
+            }
+            bm25_pack_tfn_kernel<<<t->sm_count * 8, 256>>>(t->d_doc, d_tf, t->d_fieldnorm, t->n_post, t->d_tfn);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+            cudaFree(d_tf);
         }
-        CU(cudaMemcpy(t->d_fieldnorm, fieldnorm_id, n_docs, cudaMemcpyHostToDevice));
+        // skip rows for the terms with enough postings
+        std::vector<uint32_t> skip_row(n_terms, NIDX_NIL), row_term;
+        for (uint32_t i = 0; i < n_terms; ++i)
+            if (term_off[i + 1] - term_off[i] >= (uint64_t)BM_SKIP_DF) { skip_row[i] = (uint32_t)row_term.size(); row_term.push_back(i); }
+        if (n_terms) CU(cudaMemcpy(t->d_skip_row, skip_row.data(), (size_t)n_terms * 4, cudaMemcpyHostToDevice));
+        size_t skip_words = std::max<size_t>(row_term.size(), 1) * (t->n_tiles + 1);
+        CU(cudaMalloc(&t->d_skip, skip_words * 4));
+        if (!row_term.empty()) {
+            uint32_t* d_row_term = nullptr;
+            CU(cudaMalloc(&d_row_term, row_term.size() * 4));
+            CU(cudaMemcpy(d_row_term, row_term.data(), row_term.size() * 4, cudaMemcpyHostToDevice));
+            bm25_build_skip_kernel<<<t->sm_count * 8, 256>>>(t->d_term_off, t->d_doc, d_row_term, (uint32_t)row_term.size(), t->n_tiles, t->d_skip);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+            cudaFree(d_row_term);
+        }
         t->own_df.resize(n_terms);
         for (uint32_t i = 0; i < n_terms; ++i) t->own_df[i] = term_off[i + 1] - term_off[i];
         // a segment alone only knows the quantised lengths; the exact token total comes with set_stats
@@ -962,7 +1008,7 @@ void nidx_txt_close(nidx_txt_segment* t) {
     if (!t) return;
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
-    cudaFree(t->d_term_off); cudaFree(t->d_doc); cudaFree(t->d_tf); cudaFree(t->d_fieldnorm); cudaFree(t->d_alive); cudaFree(t->d_weight);
+    cudaFree(t->d_term_off); cudaFree(t->d_doc); cudaFree(t->d_tfn); cudaFree(t->d_skip_row); cudaFree(t->d_skip); cudaFree(t->d_fieldnorm); cudaFree(t->d_alive); cudaFree(t->d_weight);
     cudaFree(t->d_norm_cache);
     delete t;
 }
@@ -1001,9 +1047,8 @@ int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint
     int shift = 24;
     while (shift > 4 && bound * (float)(1u << shift) >= 4.0e9f) --shift;
 
-    int cap = topk_cap(k, BM_THREADS);
-    int tile = 16384;
-    size_t smem = bm_smem_bytes(tile, cap);
+    int cap = next_pow2(std::max(2 * k, k + BM_THREADS * BM_ROUND));
+    size_t smem = bm_smem_bytes(cap, p->mode == NIDX_BM25_AND);
     ENSURE(w.partial, (size_t)nq * k * 8);
     ENSURE(w.misc, (size_t)nq * 8);
     uint32_t* d_docs = out_docs; float* d_sc = out_scores; int* d_cnt = out_counts;
@@ -1016,10 +1061,10 @@ int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint
         d_total = w.misc.as<unsigned long long>();
     }
     TxtDev T;
-    T.n_docs = t->n_docs; T.n_terms = t->n_terms; T.term_off = t->d_term_off; T.post_doc = t->d_doc; T.post_tf = t->d_tf; T.fieldnorm = t->d_fieldnorm;
-    T.alive = t->d_alive;
+    T.n_docs = t->n_docs; T.n_terms = t->n_terms; T.n_tiles = t->n_tiles; T.term_off = t->d_term_off; T.post_doc = t->d_doc; T.post_tfn = t->d_tfn;
+    T.skip_row = t->d_skip_row; T.skip = t->d_skip; T.alive = t->d_alive;
     Bm25Args a;
-    a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.mode = p->mode; a.use_tf = p->use_tf; a.k = k; a.cap = cap; a.tile = tile;
+    a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.mode = p->mode; a.use_tf = p->use_tf; a.k = k; a.cap = cap;
     a.term_weight = t->d_weight; a.norm_cache = t->d_norm_cache; a.shift = shift; a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total;
     CU(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bm25_kernel<<<nq, BM_THREADS, smem, stream>>>(T, a);

@@ -6,17 +6,21 @@
 // with tantivy 0.26's BM25 (restated in oracle/bm25.hpp; parity unpinned):
 //   score(doc) = sum over matching query terms of  idf_t * (1 + k1) * tf / (tf + k1 * (1 - b + b * fieldnorm / avg))
 //
-// One CTA per query walks the doc-id space in tiles of `tile` documents.  Per tile
-//   1. every query term's posting cursor is advanced to the tile end (gallop + binary search);
+// Index-time layout (bm25_prepare_* kernels, once per segment):
+//   * post_tfn[i] = tf << 8 | fieldnorm_id(doc): the document's length code travels with the posting, so
+//     scoring never gathers fieldnorm[doc] at random (one 32-byte sector per posting otherwise);
+//   * skip[row][t] = first posting of the term with doc >= t * BM_TILE, for every term with df >= BM_SKIP_DF:
+//     a query term's slice of a doc tile is two adjacent loads instead of a search.
+// Query time: one CTA per query walks the doc-id space in tiles of BM_TILE documents.  Per tile
+//   1. per-term slice bounds (skip table; gallop + binary search for rare terms), prefetched one tile ahead;
 //   2. pass 1: the tile's postings, flattened over terms, are scored and accumulated into a shared-memory
-//      accumulator with integer atomics.  Contributions are converted to fixed point (2^-shift) so the sum
-//      is independent of the order the atomics land in: equal scores stay bit-equal, which keeps the
-//      (score desc, doc asc) tie order of TopDocs deterministic;
-//   3. pass 2: the same postings are walked again; atomicExch(acc, 0) hands each touched document to
-//      exactly one thread (and leaves the accumulator clean for the next tile), which offers it to a
-//      block-wide streaming top-k.  No dense clear, no dense scan: work is proportional to postings.
-// HBM traffic = the query's postings once (doc id + tf, 8 B; 4 B when tf is not needed) + 1 B fieldnorm
-// gather per posting; everything else stays in shared memory / L1.
+//      accumulator with integer atomics.  Contributions are fixed point (2^-shift), so the sum does not
+//      depend on the order the atomics land in: equal scores stay bit-equal and the (score desc, doc asc)
+//      tie order of TopDocs is deterministic;
+//   3. pass 2: the same postings again; atomicExch(acc, 0) hands each touched document to exactly one thread
+//      (and leaves the accumulator clean for the next tile), which appends it to a streaming top-k buffer if
+//      it beats the running threshold.  Work is proportional to postings: no dense clear, no dense scan.
+// HBM traffic = the query's postings once (8 B each); everything else stays in shared memory / L1 / L2.
 #pragma once
 #include "common.cuh"
 #include "topk.cuh"
@@ -25,13 +29,18 @@ namespace nidx {
 
 constexpr int BM_THREADS = 256;
 constexpr int BM_MAX_TERMS = 128;
+constexpr int BM_TILE = 12288;     // documents per tile (48 KB of u32 accumulators; 3 CTAs per SM)
+constexpr int BM_SKIP_DF = 32;     // terms with at least this many postings get a skip row
+constexpr int BM_ROUND = 2;        // postings per thread in flight / between two top-k capacity checks
+constexpr int BM_TOUCH_CAP = 4096; // documents hit per tile that are tracked individually (else dense scan)
 
 struct TxtDev {
-    uint32_t n_docs, n_terms;
+    uint32_t n_docs, n_terms, n_tiles;
     const uint64_t* term_off;
     const uint32_t* post_doc;
-    const uint32_t* post_tf;
-    const unsigned char* fieldnorm;
+    const uint32_t* post_tfn;        // tf << 8 | fieldnorm id
+    const uint32_t* skip_row;        // [n_terms] row in skip[] or NIL
+    const uint32_t* skip;            // [rows][n_tiles + 1] posting index relative to term_off[term]
     const uint64_t* alive;
 };
 
@@ -39,7 +48,7 @@ struct Bm25Args {
     const uint32_t* query_terms;
     const uint32_t* query_off;
     int nq;
-    int mode, use_tf, k, cap, tile;
+    int mode, use_tf, k, cap;
     const float* term_weight;   // [n_terms] idf * (1 + k1) from the collection statistics
     const float* norm_cache;    // [256] k1 * (1 - b + b * fieldnorm(id) / avg)
     int shift;                  // fixed point: 2^-shift
@@ -47,25 +56,56 @@ struct Bm25Args {
     unsigned long long* out_total;  // [nq] matching documents (Count collector)
 };
 
-__host__ __device__ __forceinline__ size_t bm_smem_bytes(int tile, int cap) {
-    return (size_t)tile * 4 + (size_t)tile + (size_t)cap * 8 + BM_MAX_TERMS * (8 + 8 + 4 + 4) + 1024 + 64;
+// ---- index-time kernels ---------------------------------------------------------------------------------
+__global__ void bm25_pack_tfn_kernel(const uint32_t* __restrict__ post_doc, const uint32_t* __restrict__ post_tf, const unsigned char* __restrict__ fieldnorm,
+                                     uint64_t n_post, uint32_t* __restrict__ post_tfn) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t tf = post_tf ? post_tf[i] : 1u;
+        if (tf > 0xFFFFFFu) tf = 0xFFFFFFu;
+        post_tfn[i] = (tf << 8) | fieldnorm[post_doc[i]];
+    }
+}
+// one thread per (skip row, tile boundary)
+__global__ void bm25_build_skip_kernel(const uint64_t* __restrict__ term_off, const uint32_t* __restrict__ post_doc, const uint32_t* __restrict__ row_term,
+                                       uint32_t n_rows, uint32_t n_tiles, uint32_t* __restrict__ skip) {
+    uint64_t total = (uint64_t)n_rows * (n_tiles + 1);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t row = (uint32_t)(i / (n_tiles + 1)), t = (uint32_t)(i % (n_tiles + 1));
+        uint32_t term = row_term[row];
+        uint64_t b = term_off[term], e = term_off[term + 1];
+        uint64_t bound = (uint64_t)t * BM_TILE;
+        uint64_t l = b, r = e;
+        while (l < r) {
+            uint64_t m = (l + r) >> 1;
+            if ((uint64_t)post_doc[m] < bound) l = m + 1; else r = m;
+        }
+        skip[i] = (uint32_t)(l - b);
+    }
+}
+
+__host__ __device__ __forceinline__ size_t bm_smem_bytes(int cap, bool conj) {
+    return (size_t)BM_TILE * 4 + (conj ? (size_t)BM_TILE : 0) + (size_t)cap * 8 + (size_t)BM_TOUCH_CAP * 2 + BM_MAX_TERMS * (8 + 8 + 8 + 4 + 4 + 4 + 4) + 1024 + 64;
 }
 
 __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int tk_count;
     __shared__ uint64_t tk_thr;
-    __shared__ int s_total;
+    __shared__ int s_total, s_min_count, s_ntouched;
     __shared__ unsigned long long s_hits;
     unsigned char* p = smem;
     uint64_t* tk_buf = reinterpret_cast<uint64_t*>(p); p += (size_t)a.cap * 8;
-    uint64_t* cur = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;     // cursor per term (absolute posting index)
-    uint64_t* tend = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;    // end of the term's postings
-    uint32_t* acc = reinterpret_cast<uint32_t*>(p); p += (size_t)a.tile * 4;
+    uint64_t* tbase = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;   // term_off[term]
+    uint64_t* tend = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;    // term_off[term + 1]
+    uint64_t* cur = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;     // this tile's first posting (absolute)
+    uint32_t* acc = reinterpret_cast<uint32_t*>(p); p += (size_t)BM_TILE * 4;
     float* ncache = reinterpret_cast<float*>(p); p += 1024;
     int* pre = reinterpret_cast<int*>(p); p += BM_MAX_TERMS * 4;               // exclusive prefix of per-term counts in the tile
     float* tw = reinterpret_cast<float*>(p); p += BM_MAX_TERMS * 4;
-    uint32_t* cnt32 = reinterpret_cast<uint32_t*>(p);                          // [tile/4] packed byte counters (AND)
+    uint32_t* srow = reinterpret_cast<uint32_t*>(p); p += BM_MAX_TERMS * 4;     // skip row or NIL
+    int* cnt_t = reinterpret_cast<int*>(p); p += BM_MAX_TERMS * 4;
+    unsigned short* touched = reinterpret_cast<unsigned short*>(p); p += (size_t)BM_TOUCH_CAP * 2;   // tile-relative ids of the docs hit in this tile
+    unsigned char* cnt8 = p;                                                   // [BM_TILE] matched-term counters (AND only)
 
     int q = blockIdx.x;
     const uint32_t* terms = a.query_terms + a.query_off[q];
@@ -74,94 +114,141 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) 
     BlockTopK tk;
     tk.init(tk_buf, &tk_count, &tk_thr, a.k, a.cap);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) ncache[i] = a.norm_cache[i];
-    for (int i = threadIdx.x; i < a.tile; i += blockDim.x) acc[i] = 0;
-    for (int i = threadIdx.x; i < a.tile / 4; i += blockDim.x) cnt32[i] = 0;
+    for (int i = threadIdx.x; i < BM_TILE; i += blockDim.x) acc[i] = 0;
+    if (a.mode == 1) for (int i = threadIdx.x; i < BM_TILE / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(cnt8)[i] = 0;
     bool missing = false;
+    unsigned int my_hits = 0;  // matching documents claimed by this thread (one shared atomic per warp at the end, not per hit)
+    uint64_t my_next = 0;      // first posting of the current tile for my term
+    uint32_t pf_end = 0;       // skip[row][tile + 1], loaded one tile ahead
+    size_t my_skip = 0;
     if (threadIdx.x < nt) {
         uint32_t t = terms[threadIdx.x];
         bool ok = t < T.n_terms;
-        cur[threadIdx.x] = ok ? T.term_off[t] : 0;
-        tend[threadIdx.x] = ok ? T.term_off[t + 1] : 0;
+        uint64_t b = ok ? T.term_off[t] : 0, e = ok ? T.term_off[t + 1] : 0;
+        tbase[threadIdx.x] = b;
+        tend[threadIdx.x] = e;
         tw[threadIdx.x] = ok ? a.term_weight[t] : 0.0f;
-        missing = !ok || T.term_off[t] == T.term_off[t + 1];
+        uint32_t row = ok ? T.skip_row[t] : NIL;
+        srow[threadIdx.x] = row;
+        missing = b == e;
+        my_next = b;
+        if (row != NIL) { my_skip = (size_t)row * (T.n_tiles + 1); pf_end = T.skip[my_skip + 1]; }
     }
-    if (threadIdx.x == 0) s_hits = 0;
-    // an AND query with a term that has no postings matches nothing
-    int any_missing = __syncthreads_or(missing);
+    if (threadIdx.x == 0) { s_hits = 0; s_ntouched = 0; }
+    int any_missing = __syncthreads_or(missing);   // an AND query with a term without postings matches nothing
     bool dead = (a.mode == 1 && any_missing) || nt == 0;
     const float scale = (float)(1u << a.shift);
+    const int lane = threadIdx.x & 31;
 
-    for (uint32_t lo = 0; lo < T.n_docs && !dead; lo += a.tile) {
-        uint32_t hi = lo + a.tile < T.n_docs ? lo + a.tile : T.n_docs;
-        // 1. advance cursors to the first posting with doc >= hi
-        uint64_t my_begin = 0, my_end = 0;
+    for (uint32_t tile = 0; tile < T.n_tiles && !dead; ++tile) {
+        uint32_t lo = tile * BM_TILE;
+        uint32_t hi = lo + BM_TILE < T.n_docs ? lo + BM_TILE : T.n_docs;
+        // 1. slice [begin, end) of every term in this tile (skip entry prefetched during the previous tile)
         if (threadIdx.x < nt) {
-            uint64_t b = cur[threadIdx.x], e = tend[threadIdx.x];
-            my_begin = b;
-            uint64_t step = 32, l = b, r = e;
-            while (l + step < e && T.post_doc[l + step] < hi) { l += step; step <<= 1; }  // gallop
-            r = l + step < e ? l + step : e;
-            // invariant: every posting before l is < hi (or l == b); first posting >= hi lies in [l, r]
-            while (l < r) {
-                uint64_t m = (l + r) >> 1;
-                if (T.post_doc[m] < hi) l = m + 1; else r = m;
+            uint64_t b = my_next, e = tend[threadIdx.x], end;
+            if (srow[threadIdx.x] != NIL) {
+                end = tbase[threadIdx.x] + pf_end;
+                if (tile + 2 <= T.n_tiles) pf_end = T.skip[my_skip + tile + 2];
+            } else {                                                       // rare term: a few postings in total
+                uint64_t l = b;
+                while (l < e && T.post_doc[l] < hi) ++l;
+                end = l;
             }
-            my_end = l;
-            pre[threadIdx.x] = (int)(my_end - my_begin);
+            cur[threadIdx.x] = b;
+            cnt_t[threadIdx.x] = (int)(end - b);
+            my_next = end;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {  // tiny exclusive scan (nt <= 128)
-            int run = 0;
-            for (int t = 0; t < nt; ++t) { int c = pre[t]; pre[t] = run; run += c; }
-            s_total = run;
+        if (threadIdx.x < 32) {   // exclusive scan of the per-term counts by one warp (nt <= 128)
+            int run = 0, mn = INT_MAX;
+            for (int t0 = 0; t0 < nt; t0 += 32) {
+                int t = t0 + threadIdx.x;
+                int v = t < nt ? cnt_t[t] : 0;
+                if (t < nt && v < mn) mn = v;
+                int x = v;
+                for (int off = 1; off < 32; off <<= 1) { int y = __shfl_up_sync(0xFFFFFFFFu, x, off); if ((int)threadIdx.x >= off) x += y; }
+                if (t < nt) pre[t] = run + x - v;
+                run += __shfl_sync(0xFFFFFFFFu, x, 31);
+            }
+            for (int off = 16; off >= 1; off >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, off));
+            if (threadIdx.x == 0) { s_total = run; s_min_count = mn; }
         }
         __syncthreads();
         int total = s_total;
-        // 2. pass 1: accumulate
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            int l = 0, r = nt - 1;  // last term with pre[t] <= i
-            while (l < r) { int m = (l + r + 1) >> 1; if (pre[m] <= i) l = m; else r = m - 1; }
-            uint64_t pi = cur[l] + (uint64_t)(i - pre[l]);
-            uint32_t d = T.post_doc[pi];
-            uint32_t tf = a.use_tf ? T.post_tf[pi] : 1u;
-            float tff = (float)tf;
-            float s = __fmul_rn(tw[l], __fdiv_rn(tff, __fadd_rn(tff, ncache[T.fieldnorm[d]])));
-            uint32_t fx = (uint32_t)__float2uint_rn(__fmul_rn(s, scale));
-            if (fx == 0) fx = 1;
-            atomicAdd(&acc[d - lo], fx);
-            if (a.mode == 1) atomicAdd(&cnt32[(d - lo) >> 2], 1u << (8 * ((d - lo) & 3)));
+        if (total == 0 || (a.mode == 1 && s_min_count == 0)) continue;   // AND: some term has nothing in this tile
+        // 2. pass 1: score + accumulate; the first thread to touch a document records it
+        for (int base = 0; base < total; base += BM_THREADS * BM_ROUND) {
+            uint32_t d[BM_ROUND], tfn[BM_ROUND];
+            int tl[BM_ROUND];
+#pragma unroll
+            for (int u = 0; u < BM_ROUND; ++u) {   // all loads first: BM_ROUND postings in flight per thread
+                int i = base + u * BM_THREADS + threadIdx.x;
+                tl[u] = -1;
+                if (i < total) {
+                    int l = 0, r = nt - 1;  // last term with pre[t] <= i
+                    while (l < r) { int m = (l + r + 1) >> 1; if (pre[m] <= i) l = m; else r = m - 1; }
+                    uint64_t pi = cur[l] + (uint64_t)(i - pre[l]);
+                    d[u] = __ldg(T.post_doc + pi);
+                    tfn[u] = __ldg(T.post_tfn + pi);
+                    tl[u] = l;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BM_ROUND; ++u) {
+                bool first = false;
+                uint32_t off = 0;
+                if (tl[u] >= 0) {
+                    float tff = a.use_tf ? (float)(tfn[u] >> 8) : 1.0f;
+                    float s = __fmul_rn(tw[tl[u]], __fdiv_rn(tff, __fadd_rn(tff, ncache[tfn[u] & 0xFFu])));
+                    uint32_t fx = (uint32_t)__float2uint_rn(__fmul_rn(s, scale));
+                    if (fx == 0) fx = 1;
+                    off = d[u] - lo;
+                    first = atomicAdd(&acc[off], fx) == 0;   // fx >= 1, so a zero means nobody was here before
+                    if (a.mode == 1) atomicAdd(reinterpret_cast<uint32_t*>(cnt8) + (off >> 2), 1u << (8 * (off & 3)));
+                }
+                unsigned m = __ballot_sync(0xFFFFFFFFu, first);   // warp-aggregated append to the touched list
+                if (m) {
+                    int basepos = 0;
+                    if (lane == 0) basepos = atomicAdd(&s_ntouched, __popc(m));
+                    basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+                    int pos = basepos + __popc(m & ((1u << lane) - 1));
+                    if (first && pos < BM_TOUCH_CAP) touched[pos] = (unsigned short)off;
+                }
+            }
         }
         __syncthreads();
-        // 3. pass 2: claim + offer (lock-step rounds, BlockTopK::offer synchronises)
-        for (int base = 0; base < total; base += blockDim.x) {
-            int i = base + threadIdx.x;
-            uint64_t key = 0;
-            if (i < total) {
-                int l = 0, r = nt - 1;
-                while (l < r) { int m = (l + r + 1) >> 1; if (pre[m] <= i) l = m; else r = m - 1; }
-                uint64_t pi = cur[l] + (uint64_t)(i - pre[l]);
-                uint32_t d = T.post_doc[pi];
-                uint32_t v = atomicExch(&acc[d - lo], 0u);
-                if (v != 0) {
-                    bool match = true;
-                    if (a.mode == 1) {
-                        uint32_t sh = 8 * ((d - lo) & 3);
-                        uint32_t c = (atomicAnd(&cnt32[(d - lo) >> 2], ~(0xFFu << sh)) >> sh) & 0xFFu;
-                        match = (int)c == nt;
-                    }
-                    if (match && T.alive) match = (T.alive[d >> 6] >> (d & 63)) & 1;
-                    if (match) {
-                        atomicAdd(&s_hits, 1ull);
-                        key = make_key(__fdiv_rn((float)v, scale), d, 0);
+        // 3. pass 2: every touched document once -> count, reset, offer to the streaming top-k
+        int ntouched = s_ntouched;
+        bool dense = ntouched > BM_TOUCH_CAP;      // list overflow: fall back to scanning the whole tile
+        int work = dense ? (int)(hi - lo) : ntouched;
+        for (int base = 0; base < work; base += BM_THREADS * BM_ROUND) {
+#pragma unroll
+            for (int u = 0; u < BM_ROUND; ++u) {
+                int j = base + u * BM_THREADS + threadIdx.x;
+                if (j < work) {
+                    uint32_t off = dense ? (uint32_t)j : (uint32_t)touched[j];
+                    uint32_t v = acc[off];
+                    if (v != 0) {
+                        acc[off] = 0;
+                        bool match = true;
+                        if (a.mode == 1) { match = (int)cnt8[off] == nt; cnt8[off] = 0; }
+                        uint32_t doc = lo + off;
+                        if (match && T.alive) match = (T.alive[doc >> 6] >> (doc & 63)) & 1;
+                        if (match) {
+                            my_hits++;
+                            uint64_t key = make_key(__fdiv_rn((float)v, scale), doc, 0);
+                            if (key > tk_thr) tk_buf[atomicAdd(&tk_count, 1)] = key;
+                        }
                     }
                 }
             }
-            tk.offer(key);
+            __syncthreads();
+            if (tk_count > a.cap - BM_THREADS * BM_ROUND) tk.flush();
         }
-        __syncthreads();
-        if (threadIdx.x < nt) cur[threadIdx.x] = my_end;
-        __syncthreads();
+        if (threadIdx.x == 0) s_ntouched = 0;
     }
+    for (int off = 16; off >= 1; off >>= 1) my_hits += __shfl_xor_sync(0xFFFFFFFFu, my_hits, off);
+    if (lane == 0 && my_hits) atomicAdd(&s_hits, (unsigned long long)my_hits);
     int c = tk.finish();
     uint64_t* out = a.out_keys + (size_t)q * a.k;
     for (int i = threadIdx.x; i < a.k; i += blockDim.x) out[i] = i < c ? tk_buf[i] : 0;

@@ -123,6 +123,72 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_scores_kernel(VecDev V, 
         if (qi < nqt && lane < nv) scores[(size_t)(q0 + qi) * V.n + v0 + lane] = mine[qi];
 }
 
+// Compile-time row length (ld == NG * 128 floats), VU vectors per warp in flight: each query float4 read from
+// shared memory feeds VU vectors (VU x fewer shared-memory bytes per FMA) and VU rows' loads overlap.
+// Same lane-blocked arithmetic as warp_dot => bit-identical scores.
+template <int NG, int VU>
+__global__ void __launch_bounds__(SCAN_WARPS * 32) scan_scores_kernel_t(VecDev V, const float* __restrict__ queries, const float* __restrict__ qnorms, int nq,
+                                                                         int n_qtiles, float* __restrict__ scores) {
+    extern __shared__ __align__(16) float qs[];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int qtile = blockIdx.x % n_qtiles;
+    uint64_t chunk = blockIdx.x / n_qtiles;
+    int q0 = qtile * SCAN_QT;
+    int nqt = min(SCAN_QT, nq - q0);
+    constexpr int ng = NG * 32;
+    for (int i = threadIdx.x; i < nqt * ng; i += blockDim.x)
+        reinterpret_cast<float4*>(qs)[i] = reinterpret_cast<const float4*>(queries + (size_t)q0 * V.ld)[i];
+    __syncthreads();
+    uint64_t v0 = (chunk * SCAN_WARPS + warp) * SCAN_VPW;
+    if (v0 >= V.n) return;
+    int nv = (int)min((uint64_t)SCAN_VPW, (uint64_t)V.n - v0);
+    float mine[SCAN_QT];
+#pragma unroll
+    for (int qi = 0; qi < SCAN_QT; ++qi) mine[qi] = 0.0f;
+    for (int j0 = 0; j0 < nv; j0 += VU) {
+        float4 va[VU][NG];
+        float vnorm[VU];
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+            uint32_t v = (uint32_t)(v0 + min(j0 + u, nv - 1));   // tail: recompute the last row, result ignored
+            const float4* a = reinterpret_cast<const float4*>(V.vecs + (size_t)v * V.ld);
+#pragma unroll
+            for (int t = 0; t < NG; ++t) va[u][t] = ldg_stream(a + t * 32 + lane);
+            vnorm[u] = V.sim == SIM_COSINE ? __ldg(V.norms + v) : 0.0f;
+        }
+#pragma unroll
+        for (int qi = 0; qi < SCAN_QT; ++qi) {
+            if (qi < nqt) {
+                const float4* b = reinterpret_cast<const float4*>(qs) + (size_t)qi * ng;
+                float acc[VU][4];
+#pragma unroll
+                for (int u = 0; u < VU; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+#pragma unroll
+                for (int t = 0; t < NG; ++t) {
+                    float4 vb = b[t * 32 + lane];
+#pragma unroll
+                    for (int u = 0; u < VU; ++u) {
+                        acc[u][0] = __fmaf_rn(va[u][t].x, vb.x, acc[u][0]);
+                        acc[u][1] = __fmaf_rn(va[u][t].y, vb.y, acc[u][1]);
+                        acc[u][2] = __fmaf_rn(va[u][t].z, vb.z, acc[u][2]);
+                        acc[u][3] = __fmaf_rn(va[u][t].w, vb.w, acc[u][3]);
+                    }
+                }
+                float qn = V.sim == SIM_COSINE ? qnorms[q0 + qi] : 0.0f;
+#pragma unroll
+                for (int u = 0; u < VU; ++u) {
+                    float ab = butterfly_sum(__fadd_rn(__fadd_rn(acc[u][0], acc[u][1]), __fadd_rn(acc[u][2], acc[u][3])));
+                    float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, vnorm[u], qn) : ab;
+                    if (lane == j0 + u) mine[qi] = s;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int qi = 0; qi < SCAN_QT; ++qi)
+        if (qi < nqt && lane < nv) scores[(size_t)(q0 + qi) * V.n + v0 + lane] = mine[qi];
+}
+
 // Per (chunk, query): best vector per alive+filtered paragraph (segment.rs:581-597), min_score (>=),
 // block top-k.  par_first == nullptr: one vector per paragraph.  partial: [nq][n_chunks][k] keys.
 // dynamic smem: cap * 8 bytes.
