@@ -317,6 +317,20 @@ class OpenSegment:
                                 None))
         return ids, scores, counts
 
+    def _raw_search(self, queries, k, filter_bits):
+        """exact scan restricted to a paragraph bitset, no min_score: per (query, paragraph) the best vector's similarity."""
+        L = _lib.load()
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        keep = np.ascontiguousarray(filter_bits, dtype=np.uint64)
+        p = VecSearchParams(k, 0, float(np.finfo(np.float32).min), 1, _lib.NIDX_METHOD_BRUTE, keep.ctypes.data, 0)
+        check(L.nidx_vec_search(self._h, ptr(queries), C.c_int32(nq), C.c_int32(queries.shape[1]), _lib.NIDX_MEM_HOST, C.byref(p), ptr(ids), ptr(scores),
+                                ptr(counts), None))
+        return ids, scores, counts
+
     def paragraph_of(self, vector_addr: int) -> int:
         return int(np.searchsorted(self.first_vec, vector_addr, side="right") - 1)
 
@@ -383,14 +397,17 @@ class VectorSearcher:
             clauses.append(_map_expression(request.filtering_formula))
         operator_and = request.filter_operator == FilterOperator.And
         query = np.asarray(request.vector, dtype=np.float32)
-        if self.config.normalize_vectors:  # searcher.rs:246-252, utils.rs:20-23
+        if self.config.normalize_vectors and self.config.vector_cardinality != VectorCardinality.Multi:  # searcher.rs:246-252, utils.rs:20-23
             mag = np.float32(0)
             for x in query:
                 mag = np.float32(mag + np.float32(x) * np.float32(x))
             query = (query / np.sqrt(mag)).astype(np.float32)
-        if len(query) != self.config.dimension:
+        multi = self.config.vector_cardinality == VectorCardinality.Multi
+        if (len(query) != self.config.dimension) if not multi else (len(query) % self.config.dimension != 0 or len(query) == 0):
             raise NidxError(-1, f"InconsistentDimensions: index_config {self.config.dimension}, vector {len(query)}")
         k = request.result_per_page
+        if self.config.vector_cardinality == VectorCardinality.Multi:
+            return self._search_multi_vector(request, clauses, operator_and, prefilter, method, ef)
         fssc = _Fssc(k, request.with_duplicates)
         if k > 0 and prefilter.kind != "none":
             for seg in self.open_segments:
@@ -403,6 +420,50 @@ class VectorSearcher:
                     fssc.add(seg.keys[p], float(s), (seg, p), vb)
         docs = [DocumentScored(pid, score, list(seg.labels[p]), seg.metadata[p]) for score, pid, (seg, p) in fssc.result()]
         return VectorSearchResponse(docs)
+
+    def _search_multi_vector(self, request, clauses, operator_and, prefilter, method, ef) -> VectorSearchResponse:
+        """searcher.rs:345-394 + multivector.rs:34-46 (MaxSim).  Every query vector is searched on its own
+        (duplicates allowed, no min_score, at least 10 results), the paragraphs found are re-scored with
+        sum_q max(0, max_v sim(v, q)) -- the per-paragraph maxima come from one exact-scan call restricted to
+        the candidate paragraphs -- then min_score (strict >), sort, truncate."""
+        d = self.config.dimension
+        k = request.result_per_page
+        qv = np.asarray(request.vector, dtype=np.float32).reshape(-1, d)
+        if self.config.normalize_vectors:
+            qv = np.stack([self._normalize(v) for v in qv])
+        if k <= 0 or prefilter.kind == "none":
+            return VectorSearchResponse([])
+        first_k = max(k, 10)
+        scored = []
+        for seg in self.open_segments:
+            if request.segment_filtering_formula is not None and not _segment_matches(request.segment_filtering_formula, seg.tags):
+                continue
+            ids, _, counts = seg.search_batch(qv, first_k, float(np.finfo(np.float32).min), True, clauses, operator_and, method, ef)
+            cand = sorted({seg.paragraph_of(int(a)) for qi in range(len(qv)) for a in ids[qi, : counts[qi]]})
+            if not cand:
+                continue
+            mask = np.zeros(seg.records, dtype=bool)
+            mask[cand] = True
+            bits = np.zeros((seg.records + 63) // 64 * 8, dtype=np.uint8)
+            pb = np.packbits(mask, bitorder="little")
+            bits[: len(pb)] = pb
+            rid, rsc, rcnt = seg._raw_search(qv, len(cand), bits.view(np.uint64))
+            maxsim = {p: np.float32(0.0) for p in cand}
+            for qi in range(len(qv)):
+                best = {seg.paragraph_of(int(a)): np.float32(sc) for a, sc in zip(rid[qi, : rcnt[qi]], rsc[qi, : rcnt[qi]])}
+                for p in cand:
+                    maxsim[p] = np.float32(maxsim[p] + max(np.float32(0.0), best.get(p, np.float32(0.0))))
+            scored += [(float(sc), seg, p) for p, sc in maxsim.items() if sc > request.min_score]
+        scored.sort(key=lambda t: -t[0])
+        docs = [DocumentScored(seg.keys[p], sc, list(seg.labels[p]), seg.metadata[p]) for sc, seg, p in scored[:k]]
+        return VectorSearchResponse(docs)
+
+    @staticmethod
+    def _normalize(v):
+        mag = np.float32(0)
+        for x in v:
+            mag = np.float32(mag + np.float32(x) * np.float32(x))
+        return (v / np.sqrt(mag)).astype(np.float32)
 
     @staticmethod
     def _vector_bytes(seg: OpenSegment, addr: int) -> bytes:

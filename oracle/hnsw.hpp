@@ -126,7 +126,7 @@ struct Scored {
 };
 static inline bool better(const Scored& a, const Scored& b) { return rank_key(a.score, a.id) > rank_key(b.score, b.id); }
 
-struct Counters {
+struct alignas(64) Counters {  // one cache line per thread: these are bumped on every similarity
     uint64_t n_dist = 0, n_expand = 0, n_edges_read = 0;
 };
 

@@ -169,3 +169,20 @@ def test_text_search_and_min_score():  # nidx_text/tests/test_search.rs:311-332,
     assert all((x.score.docaddr >> 32) in (0, 1) for x in r.results)
     r1 = p.search(T.DocumentSearchRequest(body="prince moon", result_per_page=1))
     assert r1.next_page and len(r1.results) == 1
+
+
+def test_maxsim():  # nidx_vector/tests/test_maxsim.rs:22-150
+    e = np.eye(5, dtype=np.float32)
+    query = np.concatenate([e[0], e[3]])
+    d0, d1, d2 = [e[1], e[2], e[4]], [e[0], e[1], e[2]], [e[0], e[2], e[3]]
+    cfg = V.VectorConfig(dimension=5, similarity=V.Similarity.Cosine, vector_cardinality=V.VectorCardinality.Multi)
+    elems = [V.Elem(f"{RID}/f/d0/0-123", d0), V.Elem(f"{RID}/f/d1/0-123", d1), V.Elem(f"{RID}/f/d2/0-123", d2)]
+    seg = V.VectorIndexer.index_elems(elems, cfg)
+    searcher = V.VectorSearcher.open(cfg, [(seg, 1)])
+    r = searcher.search(V.VectorSearchRequest(vector=query, result_per_page=1, min_score=-10.0))
+    assert len(r.documents) == 1 and r.documents[0].doc_id == f"{RID}/f/d2/0-123" and r.documents[0].score == 2.0
+    r = searcher.search(V.VectorSearchRequest(vector=query, result_per_page=10, min_score=1.5))   # min_score on the maxsim score only
+    assert len(r.documents) == 1 and r.documents[0].doc_id == f"{RID}/f/d2/0-123" and r.documents[0].score == 2.0
+    r = searcher.search(V.VectorSearchRequest(vector=query, result_per_page=2, min_score=-10.0))
+    assert [d.doc_id for d in r.documents] == [f"{RID}/f/d2/0-123", f"{RID}/f/d1/0-123"]
+    assert [d.score for d in r.documents] == [2.0, 1.0]
