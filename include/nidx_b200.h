@@ -127,9 +127,11 @@ int nidx_vec_search(nidx_vec_segment* seg, const float* queries, int32_t nq, int
 
 /* Searcher::_search's cross-segment / cross-shard top-k (searcher.rs:241-290 Fssc without the string
  * keys, shard_merge.rs:332-348): merge n_parts partial results [n_parts][nq][k] (score desc) into
- * [nq][k]; out_part[nq][k] receives the index of the part each winner came from.  Device pointers. */
-int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int32_t nq, int32_t k, uint32_t* out_ids,
-                    float* out_scores, int32_t* out_part, void* stream);
+ * [nq][k]; out_part[nq][k] receives the index of the part each winner came from.  part_stride = elements
+ * between consecutive parts in ids / scores (0 = nq*k, i.e. dense), so an all-gather buffer can be merged in place.
+ * Device pointers. */
+int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int64_t part_stride, int32_t nq, int32_t k,
+                    uint32_t* out_ids, float* out_scores, int32_t* out_part, void* stream);
 
 /* Counters of the last HNSW search / build on this segment (for the roofline accounting,
  * SURVEY 8d): [0] similarity evaluations, [1] node expansions, [2] visited-set overflows. */

@@ -627,15 +627,15 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
     return 0;
 }
 
-int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int32_t nq, int32_t k, uint32_t* out_ids,
-                    float* out_scores, int32_t* out_part, void* stream_) {
+int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int64_t part_stride, int32_t nq, int32_t k,
+                    uint32_t* out_ids, float* out_scores, int32_t* out_part, void* stream_) {
     int r = check_device(device);
     if (r) return r;
     if (!ids || !scores || !out_ids || !out_scores || n_parts <= 0 || nq <= 0 || k <= 0) return fail(NIDX_EINVAL, "bad argument");
     if (k > 1024 || (long long)n_parts * k >= (1ll << 31)) return fail(NIDX_EINVAL, "k above 1024 not supported");
     int cap = topk_cap(k, 256);
     if ((size_t)cap * 8 > 48 * 1024) CU(cudaFuncSetAttribute(parts_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
-    parts_merge_kernel<<<nq, 256, (size_t)cap * 8, reinterpret_cast<cudaStream_t>(stream_)>>>(ids, scores, n_parts, nq, k, cap, out_ids, out_scores, out_part);
+    parts_merge_kernel<<<nq, 256, (size_t)cap * 8, reinterpret_cast<cudaStream_t>(stream_)>>>(ids, scores, n_parts, part_stride > 0 ? (size_t)part_stride : (size_t)nq * k, nq, k, cap, out_ids, out_scores, out_part);
     LAUNCHED();
     CU(cudaGetLastError());
     return 0;

@@ -254,7 +254,7 @@ __global__ void topk_merge_kernel(const uint64_t* __restrict__ keys_in, int n_in
 // Cross-part merge (searcher.rs:241-290 / shard_merge.rs:332-348): parts [n_parts][nq][k] of (id, score)
 // sorted desc -> [nq][k] plus the originating part.  Keys here rank (score desc, part asc, position asc),
 // which is what kmerge_by(|a, b| a.score >= b.score) yields for inputs that are each sorted.
-__global__ void parts_merge_kernel(const uint32_t* __restrict__ ids, const float* __restrict__ scores, int n_parts, int nq, int k, int cap,
+__global__ void parts_merge_kernel(const uint32_t* __restrict__ ids, const float* __restrict__ scores, int n_parts, size_t part_stride, int nq, int k, int cap,
                                    uint32_t* __restrict__ out_ids, float* __restrict__ out_scores, int* __restrict__ out_part) {
     extern __shared__ __align__(16) uint64_t tk_buf[];
     __shared__ int tk_count;
@@ -268,7 +268,7 @@ __global__ void parts_merge_kernel(const uint32_t* __restrict__ ids, const float
         uint64_t key = 0;
         if (i < total) {
             int part = i / k, pos = i % k;
-            size_t src = ((size_t)part * nq + q) * k + pos;
+            size_t src = (size_t)part * part_stride + (size_t)q * k + pos;
             if (ids[src] != NIL) key = make_key(scores[src], (uint32_t)i, 0);  // id field = part*k+pos
         }
         tk.offer(key);
@@ -279,7 +279,7 @@ __global__ void parts_merge_kernel(const uint32_t* __restrict__ ids, const float
         if (i < c) {
             uint32_t slot = key_id(tk_buf[i]);
             int part = slot / k, pos = slot % k;
-            size_t src = ((size_t)part * nq + q) * k + pos;
+            size_t src = (size_t)part * part_stride + (size_t)q * k + pos;
             out_ids[dst] = ids[src];
             out_scores[dst] = scores[src];
             if (out_part) out_part[dst] = part;

@@ -30,11 +30,33 @@ def global_ids(local_ids, part, vectors_per_rank: int):
     return torch.where(local_ids.to(torch.int64) < 0, torch.full_like(g, -1), g)
 
 
-def sharded_search(segment, queries, k, ef, device, group=None, **kw):
-    """Search this rank's segment, exchange partial top-k, merge on the GPU.  Returns (local ids, scores, part)."""
-    from . import _lib
-    from .segment import merge_topk
+class ShardedSearcher:
+    """One rank's view of a segment-sharded index.  Buffers are allocated once: the local result is written
+    straight into this rank's slot of the exchange buffer ([2, nq, k]: ids, score bits), ONE all_gather moves
+    every rank's slot, and parts_merge_kernel merges the gathered buffer in place (part_stride = 2*nq*k)."""
 
-    ids, scores, _ = segment.search(queries, k, ef=ef, method=_lib.NIDX_METHOD_HNSW, **kw)
-    ids_all, sc_all = gather_partials(ids, scores, group)
-    return merge_topk(ids_all, sc_all, device=device)
+    def __init__(self, segment, nq, k, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.segment, self.nq, self.k, self.device, self.group = segment, nq, k, device, group
+        self.world = dist.get_world_size(group)
+        dev = torch.device("cuda", device)
+        self.local = torch.empty((2, nq, k), dtype=torch.int32, device=dev)
+        self.counts = torch.empty((nq,), dtype=torch.int32, device=dev)
+        self.gathered = torch.empty((self.world, 2, nq, k), dtype=torch.int32, device=dev)
+        self.out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+                    torch.empty((nq, k), dtype=torch.int32, device=dev))
+
+    def search(self, queries, ef, **kw):
+        """-> (local ids, scores, part) of the merged top-k, identical on every rank."""
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        from .segment import merge_topk
+
+        self.segment.search(queries, self.k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=(self.local[0], self.local[1].view(torch.float32), self.counts), **kw)
+        dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+        g = self.gathered
+        return merge_topk(g[:, 0], g[:, 1].view(torch.float32), device=self.device, part_stride=2 * self.nq * self.k, out=self.out)

@@ -153,17 +153,18 @@ class VectorSegment:
         return dict(similarities=out[0], expansions=out[1], overflows=out[2])
 
 
-def merge_topk(ids, scores, device=0):
-    """[n_parts, nq, k] torch CUDA tensors (each part sorted desc, NIL padded) -> merged (ids, scores, part)."""
+def merge_topk(ids, scores, device=0, part_stride=0, out=None):
+    """[n_parts, nq, k] torch CUDA tensors (each part sorted desc, NIL padded) -> merged (ids, scores, part).
+    ids / scores may be strided views of one all-gather buffer: part_stride = elements between parts."""
     import torch
 
     n_parts, nq, k = ids.shape
-    out_ids = torch.empty((nq, k), dtype=ids.dtype, device=ids.device)
-    out_scores = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
-    out_part = torch.empty((nq, k), dtype=torch.int32, device=ids.device)
-    check(_lib.load().nidx_merge_topk(C.c_int32(device), ptr(ids.contiguous()), ptr(scores.contiguous()), C.c_int32(n_parts), C.c_int32(nq), C.c_int32(k),
-                                      ptr(out_ids), ptr(out_scores), ptr(out_part), _torch_stream(device)))
-    return out_ids, out_scores, out_part
+    if out is None:
+        out = (torch.empty((nq, k), dtype=ids.dtype, device=ids.device), torch.empty((nq, k), dtype=torch.float32, device=ids.device),
+               torch.empty((nq, k), dtype=torch.int32, device=ids.device))
+    check(_lib.load().nidx_merge_topk(C.c_int32(device), ptr(ids), ptr(scores), C.c_int32(n_parts), C.c_int64(part_stride), C.c_int32(nq), C.c_int32(k),
+                                      ptr(out[0]), ptr(out[1]), ptr(out[2]), _torch_stream(device)))
+    return out
 
 
 class TextSegment:

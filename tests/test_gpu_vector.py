@@ -124,3 +124,33 @@ def test_gpu_build_equals_oracle_batch_build():
     assert same_rows == 1.0
     assert np.array_equal(g["w0"], og.w0)
     assert (g["adjU"][: og.adjU.shape[0]] == og.adjU).all()
+
+
+def test_parts_merge_matches_kmerge():
+    """shard_merge.rs:332-348: kmerge_by(score >=) of per-part sorted lists, take k (ties: lower part first)."""
+    import torch
+
+    from nucliadb_b200.segment import merge_topk
+
+    rng = np.random.default_rng(5)
+    parts, nq, k = 5, 33, 10
+    sc = np.sort(rng.random((parts, nq, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    ids = rng.integers(0, 1 << 20, (parts, nq, k)).astype(np.int32)
+    ids[3, :, 6:] = -1          # a short part (NIL padded)
+    sc[3, :, 6:] = 0
+    sc[1, 0, :3] = sc[0, 0, :3]  # exact ties across parts
+    want_ids = np.empty((nq, k), np.int32)
+    want_part = np.empty((nq, k), np.int32)
+    for q in range(nq):
+        items = sorted(((-float(sc[p, q, j]), p, j) for p in range(parts) for j in range(k) if ids[p, q, j] != -1))[:k]
+        want_ids[q] = [ids[p, q, j] for _, p, j in items]
+        want_part[q] = [p for _, p, j in items]
+    dev = torch.device("cuda", 0)
+    got = merge_topk(torch.tensor(ids, device=dev), torch.tensor(sc, device=dev))
+    assert (got[0].cpu().numpy() == want_ids).all() and (got[2].cpu().numpy() == want_part).all()
+    # the same data interleaved as an all-gather buffer [parts, 2, nq, k] merged in place
+    buf = torch.empty((parts, 2, nq, k), dtype=torch.int32, device=dev)
+    buf[:, 0] = torch.tensor(ids, device=dev)
+    buf[:, 1] = torch.tensor(sc, device=dev).view(torch.int32)
+    got2 = merge_topk(buf[:, 0], buf[:, 1].view(torch.float32), part_stride=2 * nq * k)
+    assert (got2[0].cpu().numpy() == want_ids).all() and (got2[2].cpu().numpy() == want_part).all()
