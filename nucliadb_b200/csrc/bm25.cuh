@@ -84,28 +84,32 @@ __global__ void bm25_build_skip_kernel(const uint64_t* __restrict__ term_off, co
 }
 
 __host__ __device__ __forceinline__ size_t bm_smem_bytes(int cap, bool conj) {
-    return (size_t)BM_TILE * 4 + (conj ? (size_t)BM_TILE : 0) + (size_t)cap * 8 + (size_t)BM_TOUCH_CAP * 2 + BM_MAX_TERMS * (8 + 8 + 8 + 4 + 4 + 4 + 4) + 1024 + 64;
+    return (size_t)BM_TILE * 4 + (conj ? (size_t)BM_TILE : 0) + (size_t)cap * 8 + (size_t)BM_TOUCH_CAP * 2 +
+           BM_MAX_TERMS * (8 + 8 + 2 * 8 + 2 * 4 + 4 + 4 + 4) + 1024 + 64;
 }
 
+// Software pipeline over tiles: while tile t is accumulated and collected out of registers / shared memory, the
+// slices of tile t+1 are resolved (skip entries were requested two tiles earlier) and its postings are already in
+// flight from HBM, so no global-memory latency sits on the per-tile critical path.
 __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int tk_count;
     __shared__ uint64_t tk_thr;
-    __shared__ int s_total, s_min_count, s_ntouched;
+    __shared__ int s_total[2], s_min_count[2], s_ntouched[2];   // touched counters alternate with the tile parity
     __shared__ unsigned long long s_hits;
     unsigned char* p = smem;
     uint64_t* tk_buf = reinterpret_cast<uint64_t*>(p); p += (size_t)a.cap * 8;
-    uint64_t* tbase = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;   // term_off[term]
-    uint64_t* tend = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;    // term_off[term + 1]
-    uint64_t* cur = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;     // this tile's first posting (absolute)
+    uint64_t* tbase = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;       // term_off[term]
+    uint64_t* tend = reinterpret_cast<uint64_t*>(p); p += BM_MAX_TERMS * 8;        // term_off[term + 1]
+    uint64_t* cur = reinterpret_cast<uint64_t*>(p); p += 2 * BM_MAX_TERMS * 8;     // [2][terms] first posting of the tile (absolute)
     uint32_t* acc = reinterpret_cast<uint32_t*>(p); p += (size_t)BM_TILE * 4;
     float* ncache = reinterpret_cast<float*>(p); p += 1024;
-    int* pre = reinterpret_cast<int*>(p); p += BM_MAX_TERMS * 4;               // exclusive prefix of per-term counts in the tile
+    int* pre = reinterpret_cast<int*>(p); p += 2 * BM_MAX_TERMS * 4;               // [2][terms] exclusive prefix of per-term counts
     float* tw = reinterpret_cast<float*>(p); p += BM_MAX_TERMS * 4;
-    uint32_t* srow = reinterpret_cast<uint32_t*>(p); p += BM_MAX_TERMS * 4;     // skip row or NIL
+    uint32_t* srow = reinterpret_cast<uint32_t*>(p); p += BM_MAX_TERMS * 4;        // skip row or NIL
     int* cnt_t = reinterpret_cast<int*>(p); p += BM_MAX_TERMS * 4;
     unsigned short* touched = reinterpret_cast<unsigned short*>(p); p += (size_t)BM_TOUCH_CAP * 2;   // tile-relative ids of the docs hit in this tile
-    unsigned char* cnt8 = p;                                                   // [BM_TILE] matched-term counters (AND only)
+    unsigned char* cnt8 = p;                                                       // [BM_TILE] matched-term counters (AND only)
 
     int q = blockIdx.x;
     const uint32_t* terms = a.query_terms + a.query_off[q];
@@ -118,8 +122,8 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) 
     if (a.mode == 1) for (int i = threadIdx.x; i < BM_TILE / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(cnt8)[i] = 0;
     bool missing = false;
     unsigned int my_hits = 0;  // matching documents claimed by this thread (one shared atomic per warp at the end, not per hit)
-    uint64_t my_next = 0;      // first posting of the current tile for my term
-    uint32_t pf_end = 0;       // skip[row][tile + 1], loaded one tile ahead
+    uint64_t my_next = 0;      // first posting of the next unresolved tile for my term
+    uint32_t pf_end = 0;       // skip entry of the next unresolved tile's end, requested one resolve step ahead
     size_t my_skip = 0;
     if (threadIdx.x < nt) {
         uint32_t t = terms[threadIdx.x];
@@ -134,28 +138,28 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) 
         my_next = b;
         if (row != NIL) { my_skip = (size_t)row * (T.n_tiles + 1); pf_end = T.skip[my_skip + 1]; }
     }
-    if (threadIdx.x == 0) { s_hits = 0; s_ntouched = 0; }
+    if (threadIdx.x == 0) { s_hits = 0; s_ntouched[0] = 0; s_ntouched[1] = 0; }
     int any_missing = __syncthreads_or(missing);   // an AND query with a term without postings matches nothing
     bool dead = (a.mode == 1 && any_missing) || nt == 0;
     const float scale = (float)(1u << a.shift);
     const int lane = threadIdx.x & 31;
+    const uint32_t n_tiles = dead ? 0 : T.n_tiles;
 
-    for (uint32_t tile = 0; tile < T.n_tiles && !dead; ++tile) {
-        uint32_t lo = tile * BM_TILE;
-        uint32_t hi = lo + BM_TILE < T.n_docs ? lo + BM_TILE : T.n_docs;
-        // 1. slice [begin, end) of every term in this tile (skip entry prefetched during the previous tile)
+    // resolve(tile, buf): slices of every term in `tile` -> cur[buf], pre[buf], s_total[buf], s_min_count[buf]
+    auto resolve = [&](uint32_t tile, int buf) {
+        uint32_t hi = (tile + 1) * BM_TILE < T.n_docs ? (tile + 1) * BM_TILE : T.n_docs;
         if (threadIdx.x < nt) {
-            uint64_t b = my_next, e = tend[threadIdx.x], end;
+            uint64_t bgn = my_next, e = tend[threadIdx.x], end;
             if (srow[threadIdx.x] != NIL) {
                 end = tbase[threadIdx.x] + pf_end;
                 if (tile + 2 <= T.n_tiles) pf_end = T.skip[my_skip + tile + 2];
             } else {                                                       // rare term: a few postings in total
-                uint64_t l = b;
+                uint64_t l = bgn;
                 while (l < e && T.post_doc[l] < hi) ++l;
                 end = l;
             }
-            cur[threadIdx.x] = b;
-            cnt_t[threadIdx.x] = (int)(end - b);
+            cur[buf * BM_MAX_TERMS + threadIdx.x] = bgn;
+            cnt_t[threadIdx.x] = (int)(end - bgn);
             my_next = end;
         }
         __syncthreads();
@@ -167,85 +171,118 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) 
                 if (t < nt && v < mn) mn = v;
                 int x = v;
                 for (int off = 1; off < 32; off <<= 1) { int y = __shfl_up_sync(0xFFFFFFFFu, x, off); if ((int)threadIdx.x >= off) x += y; }
-                if (t < nt) pre[t] = run + x - v;
+                if (t < nt) pre[buf * BM_MAX_TERMS + t] = run + x - v;
                 run += __shfl_sync(0xFFFFFFFFu, x, 31);
             }
             for (int off = 16; off >= 1; off >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, off));
-            if (threadIdx.x == 0) { s_total = run; s_min_count = mn; }
+            if (threadIdx.x == 0) { s_total[buf] = run; s_min_count[buf] = mn; }
         }
         __syncthreads();
-        int total = s_total;
-        if (total == 0 || (a.mode == 1 && s_min_count == 0)) continue;   // AND: some term has nothing in this tile
-        // 2. pass 1: score + accumulate; the first thread to touch a document records it
-        for (int base = 0; base < total; base += BM_THREADS * BM_ROUND) {
-            uint32_t d[BM_ROUND], tfn[BM_ROUND];
-            int tl[BM_ROUND];
+    };
+    // fetch(buf): this thread's first BM_ROUND postings of the tile resolved in `buf` -> registers (loads in flight)
+    uint32_t d_n[BM_ROUND], tfn_n[BM_ROUND], d_c[BM_ROUND], tfn_c[BM_ROUND];
+    int tl_n[BM_ROUND], tl_c[BM_ROUND];
+    auto locate = [&](int buf, int i, int& l) -> uint64_t {
+        const int* pr = pre + buf * BM_MAX_TERMS;
+        int lo_ = 0, r = nt - 1;  // last term with pre[t] <= i
+        while (lo_ < r) { int m = (lo_ + r + 1) >> 1; if (pr[m] <= i) lo_ = m; else r = m - 1; }
+        l = lo_;
+        return cur[buf * BM_MAX_TERMS + lo_] + (uint64_t)(i - pr[lo_]);
+    };
+    auto fetch = [&](int buf) {
+        int total = s_total[buf];
+        bool skip_tile = total == 0 || (a.mode == 1 && s_min_count[buf] == 0);
 #pragma unroll
-            for (int u = 0; u < BM_ROUND; ++u) {   // all loads first: BM_ROUND postings in flight per thread
-                int i = base + u * BM_THREADS + threadIdx.x;
-                tl[u] = -1;
-                if (i < total) {
-                    int l = 0, r = nt - 1;  // last term with pre[t] <= i
-                    while (l < r) { int m = (l + r + 1) >> 1; if (pre[m] <= i) l = m; else r = m - 1; }
-                    uint64_t pi = cur[l] + (uint64_t)(i - pre[l]);
-                    d[u] = __ldg(T.post_doc + pi);
-                    tfn[u] = __ldg(T.post_tfn + pi);
-                    tl[u] = l;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BM_ROUND; ++u) {
-                bool first = false;
-                uint32_t off = 0;
-                if (tl[u] >= 0) {
-                    float tff = a.use_tf ? (float)(tfn[u] >> 8) : 1.0f;
-                    float s = __fmul_rn(tw[tl[u]], __fdiv_rn(tff, __fadd_rn(tff, ncache[tfn[u] & 0xFFu])));
-                    uint32_t fx = (uint32_t)__float2uint_rn(__fmul_rn(s, scale));
-                    if (fx == 0) fx = 1;
-                    off = d[u] - lo;
-                    first = atomicAdd(&acc[off], fx) == 0;   // fx >= 1, so a zero means nobody was here before
-                    if (a.mode == 1) atomicAdd(reinterpret_cast<uint32_t*>(cnt8) + (off >> 2), 1u << (8 * (off & 3)));
-                }
-                unsigned m = __ballot_sync(0xFFFFFFFFu, first);   // warp-aggregated append to the touched list
-                if (m) {
-                    int basepos = 0;
-                    if (lane == 0) basepos = atomicAdd(&s_ntouched, __popc(m));
-                    basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
-                    int pos = basepos + __popc(m & ((1u << lane) - 1));
-                    if (first && pos < BM_TOUCH_CAP) touched[pos] = (unsigned short)off;
-                }
+        for (int u = 0; u < BM_ROUND; ++u) {
+            int i = u * BM_THREADS + threadIdx.x;
+            tl_n[u] = -1;
+            if (!skip_tile && i < total) {
+                int l;
+                uint64_t pi = locate(buf, i, l);
+                d_n[u] = __ldg(T.post_doc + pi);
+                tfn_n[u] = __ldg(T.post_tfn + pi);
+                tl_n[u] = l;
             }
         }
-        __syncthreads();
-        // 3. pass 2: every touched document once -> count, reset, offer to the streaming top-k
-        int ntouched = s_ntouched;
-        bool dense = ntouched > BM_TOUCH_CAP;      // list overflow: fall back to scanning the whole tile
-        int work = dense ? (int)(hi - lo) : ntouched;
-        for (int base = 0; base < work; base += BM_THREADS * BM_ROUND) {
+    };
+    auto accumulate = [&](uint32_t lo, uint32_t d, uint32_t tfn, int l, int par) {
+        bool first = false;
+        uint32_t off = 0;
+        if (l >= 0) {
+            float tff = a.use_tf ? (float)(tfn >> 8) : 1.0f;
+            float s = __fmul_rn(tw[l], __fdiv_rn(tff, __fadd_rn(tff, ncache[tfn & 0xFFu])));
+            uint32_t fx = (uint32_t)__float2uint_rn(__fmul_rn(s, scale));
+            if (fx == 0) fx = 1;
+            off = d - lo;
+            first = atomicAdd(&acc[off], fx) == 0;   // fx >= 1, so a zero means nobody was here before
+            if (a.mode == 1) atomicAdd(reinterpret_cast<uint32_t*>(cnt8) + (off >> 2), 1u << (8 * (off & 3)));
+        }
+        unsigned m = __ballot_sync(0xFFFFFFFFu, first);   // warp-aggregated append to the touched list
+        if (m) {
+            int basepos = 0;
+            if (lane == 0) basepos = atomicAdd(&s_ntouched[par], __popc(m));
+            basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+            int pos = basepos + __popc(m & ((1u << lane) - 1));
+            if (first && pos < BM_TOUCH_CAP) touched[pos] = (unsigned short)off;
+        }
+    };
+
+    if (n_tiles) { resolve(0, 0); fetch(0); }
 #pragma unroll
-            for (int u = 0; u < BM_ROUND; ++u) {
-                int j = base + u * BM_THREADS + threadIdx.x;
-                if (j < work) {
-                    uint32_t off = dense ? (uint32_t)j : (uint32_t)touched[j];
-                    uint32_t v = acc[off];
-                    if (v != 0) {
-                        acc[off] = 0;
-                        bool match = true;
-                        if (a.mode == 1) { match = (int)cnt8[off] == nt; cnt8[off] = 0; }
-                        uint32_t doc = lo + off;
-                        if (match && T.alive) match = (T.alive[doc >> 6] >> (doc & 63)) & 1;
-                        if (match) {
-                            my_hits++;
-                            uint64_t key = make_key(__fdiv_rn((float)v, scale), doc, 0);
-                            if (key > tk_thr) tk_buf[atomicAdd(&tk_count, 1)] = key;
+    for (int u = 0; u < BM_ROUND; ++u) { d_c[u] = d_n[u]; tfn_c[u] = tfn_n[u]; tl_c[u] = tl_n[u]; }
+
+    for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        int cb = tile & 1, nb = cb ^ 1;
+        uint32_t lo = tile * BM_TILE;
+        uint32_t hi = lo + BM_TILE < T.n_docs ? lo + BM_TILE : T.n_docs;
+        if (tile + 1 < n_tiles) { resolve(tile + 1, nb); fetch(nb); }   // next tile's postings now in flight
+        int total = s_total[cb];
+        bool do_tile = !(total == 0 || (a.mode == 1 && s_min_count[cb] == 0));   // AND: some term has nothing in this tile
+        if (do_tile) {
+            // pass 1: score + accumulate (registers first, then whatever did not fit the prefetch window)
+#pragma unroll
+            for (int u = 0; u < BM_ROUND; ++u) accumulate(lo, d_c[u], tfn_c[u], tl_c[u], cb);
+            for (int base = BM_THREADS * BM_ROUND; base < total; base += BM_THREADS) {
+                int i = base + threadIdx.x, l = -1;
+                uint32_t d = 0, tfn = 0;
+                if (i < total) { uint64_t pi = locate(cb, i, l); d = __ldg(T.post_doc + pi); tfn = __ldg(T.post_tfn + pi); }
+                accumulate(lo, d, tfn, l, cb);
+            }
+            __syncthreads();
+            // pass 2: every touched document once -> count, reset, offer to the streaming top-k
+            int ntouched = s_ntouched[cb];
+            bool dense = ntouched > BM_TOUCH_CAP;      // list overflow: fall back to scanning the whole tile
+            int work = dense ? (int)(hi - lo) : ntouched;
+            for (int base = 0; base < work; base += BM_THREADS * BM_ROUND) {
+#pragma unroll
+                for (int u = 0; u < BM_ROUND; ++u) {
+                    int j = base + u * BM_THREADS + threadIdx.x;
+                    if (j < work) {
+                        uint32_t off = dense ? (uint32_t)j : (uint32_t)touched[j];
+                        uint32_t v = acc[off];
+                        if (v != 0) {
+                            acc[off] = 0;
+                            bool match = true;
+                            if (a.mode == 1) { match = (int)cnt8[off] == nt; cnt8[off] = 0; }
+                            uint32_t doc = lo + off;
+                            if (match && T.alive) match = (T.alive[doc >> 6] >> (doc & 63)) & 1;
+                            if (match) {
+                                my_hits++;
+                                uint64_t key = make_key(__fdiv_rn((float)v, scale), doc, 0);
+                                if (key > tk_thr) tk_buf[atomicAdd(&tk_count, 1)] = key;
+                            }
                         }
                     }
                 }
+                __syncthreads();
+                if (tk_count > a.cap - BM_THREADS * BM_ROUND) tk.flush();
             }
-            __syncthreads();
-            if (tk_count > a.cap - BM_THREADS * BM_ROUND) tk.flush();
+            // reset after everyone has read it (the loop above synchronised at least once iff ntouched > 0); the next
+            // user of this parity is tile + 2, behind the barriers of the next iteration's resolve()
+            if (threadIdx.x == 0 && ntouched > 0) s_ntouched[cb] = 0;
         }
-        if (threadIdx.x == 0) s_ntouched = 0;
+#pragma unroll
+        for (int u = 0; u < BM_ROUND; ++u) { d_c[u] = d_n[u]; tfn_c[u] = tfn_n[u]; tl_c[u] = tl_n[u]; }
     }
     for (int off = 16; off >= 1; off >>= 1) my_hits += __shfl_xor_sync(0xFFFFFFFFu, my_hits, off);
     if (lane == 0 && my_hits) atomicAdd(&s_hits, (unsigned long long)my_hits);
