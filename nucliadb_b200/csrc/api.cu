@@ -19,6 +19,7 @@
 #include "hnsw_build.cuh"
 #include "hnsw_search.cuh"
 #include "scan.cu"
+#include "scan_tc.cuh"
 #include "segment_io.hpp"
 #include "topk.cuh"
 
@@ -563,6 +564,11 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
         ENSURE(w.partial, (size_t)qgroup * n_chunks * k * 8);
         size_t smem_scan = (size_t)SCAN_QT * s->ld * 4;
         scan_kernel_t scan_kern = pick_scan_kernel(s->ld);
+        // Batches of >= 128 queries go to the tensor cores (scores within ~3e-7 of the lane-blocked order);
+        // NIDX_B200_SCAN=exact forces the bit-exact CUDA-core kernel, =tensor forces the tensor path.
+        const char* scan_env = getenv("NIDX_B200_SCAN");
+        bool tensor_scan = s->ld % TC_KB == 0 && ((nq >= 128 && !(scan_env && !strcmp(scan_env, "exact"))) || (scan_env && !strcmp(scan_env, "tensor")));
+        if (tensor_scan) CU(cudaFuncSetAttribute(scan_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         if (smem_scan > 48 * 1024) CU(cudaFuncSetAttribute(scan_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         if ((size_t)cap * 8 > 48 * 1024) {
             CU(cudaFuncSetAttribute(scan_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
@@ -575,8 +581,14 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
             uint64_t grid = n_vchunks * n_qtiles;
             if (grid > 0x7FFFFFFFull) return fail(NIDX_EINVAL, "scan grid too large");
             if (q0 == 0) CU(cudaEventRecord(s->ev_k0, stream));
-            scan_kern<<<(unsigned)grid, SCAN_WARPS * 32, smem_scan, stream>>>(V, dq + (size_t)q0 * s->ld, w.qnorms.as<float>() + q0, nqg, n_qtiles,
+            if (tensor_scan) {
+                // large batch: the score matrix is a dense GEMM -> tcgen05 (3xTF32, f32 accumulate in TMEM)
+                dim3 tgrid((unsigned)((s->n + TC_N - 1) / TC_N), (unsigned)((nqg + TC_M - 1) / TC_M));
+                scan_scores_tc_kernel<<<tgrid, TC_THREADS, TC_SMEM_BYTES, stream>>>(V, dq + (size_t)q0 * s->ld, w.qnorms.as<float>() + q0, nqg, w.scores.as<float>());
+            } else {
+                scan_kern<<<(unsigned)grid, SCAN_WARPS * 32, smem_scan, stream>>>(V, dq + (size_t)q0 * s->ld, w.qnorms.as<float>() + q0, nqg, n_qtiles,
                                                                                      w.scores.as<float>());
+            }
             if (q0 == 0) CU(cudaEventRecord(s->ev_k1, stream));
             LAUNCHED();
             scan_select_kernel<<<dim3(n_chunks, nqg), 256, (size_t)cap * 8, stream>>>(w.scores.as<float>(), (uint32_t)s->n, s->n_par, s->d_par_first, nullptr, bits,

@@ -154,3 +154,23 @@ def test_parts_merge_matches_kmerge():
     buf[:, 1] = torch.tensor(sc, device=dev).view(torch.int32)
     got2 = merge_topk(buf[:, 0], buf[:, 1].view(torch.float32), part_stride=2 * nq * k)
     assert (got2[0].cpu().numpy() == want_ids).all() and (got2[2].cpu().numpy() == want_part).all()
+
+
+@pytest.mark.parametrize("sim", [_lib.NIDX_SIM_COSINE, _lib.NIDX_SIM_DOT])
+def test_tensor_core_scan_within_tolerance(sim, monkeypatch):
+    """Batches >= 128 queries use the tcgen05 3xTF32 kernel: similarities within 1e-5 of the oracle, ids equal wherever the
+    oracle's neighbouring scores are further apart than the tolerance; NIDX_B200_SCAN=exact gives the bit-exact kernel."""
+    v = make_vectors(20000, 384, seed=8)
+    q = make_queries(v, 256)
+    seg = _seg(v, sim)
+    oi, os_, oc = O.brute_force(v, q, 10, sim=sim, nthreads=8)
+    monkeypatch.setenv("NIDX_B200_SCAN", "tensor")
+    ids, sc, cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+    assert (cnt == oc).all()
+    assert np.abs(sc - os_).max() <= 1e-5
+    gaps = np.abs(np.diff(os_, axis=1)) > 2e-5
+    strict = np.concatenate([np.ones((len(q), 1), bool), gaps], 1) & np.concatenate([gaps, np.ones((len(q), 1), bool)], 1)
+    assert (ids[strict] == oi[strict]).all() and (ids == oi).mean() > 0.99
+    monkeypatch.setenv("NIDX_B200_SCAN", "exact")
+    ids, sc, cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+    assert (ids == oi).all() and np.array_equal(sc, os_)
