@@ -174,3 +174,32 @@ def test_tensor_core_scan_within_tolerance(sim, monkeypatch):
     monkeypatch.setenv("NIDX_B200_SCAN", "exact")
     ids, sc, cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
     assert (ids == oi).all() and np.array_equal(sc, os_)
+
+
+def test_search_is_reentrant(small_data):
+    """Searchers are shared behind an Arc and called from many blocking threads at once (index_cache.rs:41-47,
+    shard_search.rs:139-155): concurrent calls on one handle must give the sequential answers."""
+    import threading
+
+    v, q = small_data
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=100)
+    seg.build_hnsw(seed=2, max_batch=512)
+    want_h = seg.search(q, 10, ef=64, method=_lib.NIDX_METHOD_HNSW)
+    want_b = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+    errors = []
+
+    def worker(kind):
+        try:
+            for _ in range(20):
+                got = seg.search(q, 10, ef=64, method=_lib.NIDX_METHOD_HNSW) if kind else seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+                want = want_h if kind else want_b
+                assert (got[0] == want[0]).all() and np.array_equal(got[1], want[1])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i % 2,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
