@@ -168,6 +168,13 @@ typedef struct nidx_txt_search_params {
     int32_t mode;    /* NIDX_BM25_* */
     int32_t use_tf;  /* 0: IndexRecordOption::Basic (tf == 1), 1: real term frequencies */
     float min_score; /* results below are dropped after top-k (reader.rs:302-305) */
+    /* nidx_paragraph search-after (reader.rs:350-392 build_topdocs_search_after_collector / is_after): documents that
+     * are not "after" (after_score, tie break) are scored -inf by the reference's tweak_score; here they are counted
+     * in out_total but never enter the top-k. */
+    int32_t after_mode;      /* 0 = no search_after; 1 = SearchAfterTieBreak::Drop; 2 = KeepAfter(after_docaddr); 3 = Keep */
+    float after_score;       /* SearchAfter.score */
+    uint64_t after_docaddr;  /* KeepAfter payload */
+    uint64_t docaddr_base;   /* segment_ord << 32: docaddr = docaddr_base + doc (reader.rs:366-371) */
 } nidx_txt_search_params;
 
 /* nq queries; query i is query_terms[query_off[i] .. query_off[i+1]) (term ids).

@@ -46,7 +46,8 @@ class VecSearchParams(C.Structure):
 
 
 class TxtSearchParams(C.Structure):
-    _fields_ = [("k", C.c_int32), ("mode", C.c_int32), ("use_tf", C.c_int32), ("min_score", C.c_float)]
+    _fields_ = [("k", C.c_int32), ("mode", C.c_int32), ("use_tf", C.c_int32), ("min_score", C.c_float), ("after_mode", C.c_int32),
+                ("after_score", C.c_float), ("after_docaddr", C.c_uint64), ("docaddr_base", C.c_uint64)]
 
 
 _lib = None

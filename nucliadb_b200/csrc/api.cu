@@ -1077,7 +1077,8 @@ int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint
     T.skip_row = t->d_skip_row; T.skip = t->d_skip; T.alive = t->d_alive;
     Bm25Args a;
     a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.mode = p->mode; a.use_tf = p->use_tf; a.k = k; a.cap = cap;
-    a.term_weight = t->d_weight; a.norm_cache = t->d_norm_cache; a.shift = shift; a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total;
+    a.term_weight = t->d_weight; a.norm_cache = t->d_norm_cache; a.shift = shift;
+    a.after_mode = p->after_mode; a.after_score = p->after_score; a.after_docaddr = p->after_docaddr; a.docaddr_base = p->docaddr_base; a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total;
     CU(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bm25_kernel<<<nq, BM_THREADS, smem, stream>>>(T, a);
     LAUNCHED();

@@ -52,6 +52,9 @@ struct Bm25Args {
     const float* term_weight;   // [n_terms] idf * (1 + k1) from the collection statistics
     const float* norm_cache;    // [256] k1 * (1 - b + b * fieldnorm(id) / avg)
     int shift;                  // fixed point: 2^-shift
+    int after_mode;             // search-after (nidx_paragraph reader.rs:379-392): 0 none, 1 Drop, 2 KeepAfter, 3 Keep
+    float after_score;
+    uint64_t after_docaddr, docaddr_base;
     uint64_t* out_keys;         // [nq][k] rank keys (score desc, doc asc), 0 = none
     unsigned long long* out_total;  // [nq] matching documents (Count collector)
 };
@@ -268,8 +271,14 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) 
                             if (match && T.alive) match = (T.alive[doc >> 6] >> (doc & 63)) & 1;
                             if (match) {
                                 my_hits++;
-                                uint64_t key = make_key(__fdiv_rn((float)v, scale), doc, 0);
-                                if (key > tk_thr) tk_buf[atomicAdd(&tk_count, 1)] = key;
+                                float score = __fdiv_rn((float)v, scale);
+                                bool after = true;   // is_after(): strictly lower score, or an equal score that the tie break keeps
+                                if (a.after_mode != 0) {
+                                    uint32_t so = ordered_bits(score), ao = ordered_bits(a.after_score);
+                                    after = so < ao || (so == ao && (a.after_mode == 3 || (a.after_mode == 2 && a.docaddr_base + doc > a.after_docaddr)));
+                                }
+                                uint64_t key = make_key(score, doc, 0);
+                                if (after && key > tk_thr) tk_buf[atomicAdd(&tk_count, 1)] = key;
                             }
                         }
                     }

@@ -190,11 +190,14 @@ class TextSegment:
     def set_alive(self, alive_bits: Optional[np.ndarray]):
         check(_lib.load().nidx_txt_set_alive(self._h, ptr(alive_bits)))
 
-    def search(self, query_terms, query_off, k, mode=_lib.NIDX_BM25_OR, use_tf=True, min_score=0.0, out=None):
+    def search(self, query_terms, query_off, k, mode=_lib.NIDX_BM25_OR, use_tf=True, min_score=0.0, out=None, after=None, docaddr_base=0):
         """query i = query_terms[query_off[i]:query_off[i+1]].  numpy -> host path, torch CUDA int32 -> device path.
         Returns (docs, scores, counts, total)."""
         L = _lib.load()
-        p = TxtSearchParams(k, mode, int(use_tf), min_score)
+        # after = (score, mode, docaddr) with mode 1 Drop / 2 KeepAfter / 3 Keep (nidx_paragraph SearchAfter)
+        p = TxtSearchParams(k, mode, int(use_tf), min_score, 0, 0.0, 0, docaddr_base)
+        if after is not None:
+            p.after_score, p.after_mode, p.after_docaddr = float(after[0]), int(after[1]), int(after[2])
         if _is_torch(query_terms):
             import torch
 

@@ -65,6 +65,14 @@ class DocumentSearchRequest:  # nidx_text/src/request_types.rs:17-28
     result_per_page: int = 20
     min_score: float = 0.0
     only_faceted: bool = False
+    search_after: Optional[SearchAfter] = None  # ParagraphSearchRequest.search_after (nidx_paragraph only)
+
+
+@dataclass
+class SearchAfter:  # nidx_paragraph/src/request_types.rs:20-31
+    score: float
+    tie_break: str = "drop"   # "drop" | "keep" | "keep_after"
+    docaddr: int = 0          # payload of KeepAfter
 
 
 @dataclass
@@ -155,8 +163,12 @@ class TextSearcher:
         qo = np.asarray([0, len(terms)], dtype=np.uint32)
         merged = []
         for ord_, seg in enumerate(self.segments):
+            after = None
+            if request.search_after is not None:
+                sa = request.search_after
+                after = (sa.score, {"drop": 1, "keep_after": 2, "keep": 3}[sa.tie_break], sa.docaddr)
             docs, scores, counts, total = seg._gpu.search(qt, qo, k + 1, mode=_lib.NIDX_BM25_AND if self.conjunction else _lib.NIDX_BM25_OR,
-                                                          use_tf=self.use_tf, min_score=0.0)
+                                                          use_tf=self.use_tf, min_score=0.0, after=after, docaddr_base=ord_ << 32)
             resp.total += int(total[0])
             merged += [(-float(scores[0, i]), ord_, int(docs[0, i])) for i in range(int(counts[0]))]
         merged.sort()  # score desc, then segment_ord, then doc: lower docaddr first

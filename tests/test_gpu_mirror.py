@@ -186,3 +186,21 @@ def test_maxsim():  # nidx_vector/tests/test_maxsim.rs:22-150
     r = searcher.search(V.VectorSearchRequest(vector=query, result_per_page=2, min_score=-10.0))
     assert [d.doc_id for d in r.documents] == [f"{RID}/f/d2/0-123", f"{RID}/f/d1/0-123"]
     assert [d.score for d in r.documents] == [2.0, 1.0]
+
+
+def test_paragraph_search_after():  # nidx_paragraph/src/reader.rs:350-392 is_after; nidx/tests/integration/search_after.rs
+    docs = [T.TextDoc(f"r{i}", "a/title", "prince " + " ".join(["filler"] * i)) for i in range(12)]
+    p = T.ParagraphSearcher.open([docs[:6], docs[6:]])
+    full = p.search(T.DocumentSearchRequest(body="prince", result_per_page=20))
+    assert len(full.results) == 12 and full.total == 12
+    page1 = p.search(T.DocumentSearchRequest(body="prince", result_per_page=5))
+    assert page1.next_page and [r.uuid for r in page1.results] == [r.uuid for r in full.results[:5]]
+    last = page1.results[-1]
+    page2 = p.search(T.DocumentSearchRequest(body="prince", result_per_page=5, search_after=T.SearchAfter(last.score.bm25, "keep_after", last.score.docaddr)))
+    assert page2.total == 12                                   # Count still sees everything
+    got, want = [r.uuid for r in page2.results], [r.uuid for r in full.results[5:10]]
+    assert got == want
+    none = p.search(T.DocumentSearchRequest(body="prince", result_per_page=5, search_after=T.SearchAfter(full.results[-1].score.bm25, "drop")))
+    assert none.results == []
+    keep = p.search(T.DocumentSearchRequest(body="prince", result_per_page=20, search_after=T.SearchAfter(full.results[3].score.bm25, "keep")))
+    assert [r.uuid for r in keep.results] == [r.uuid for r in full.results if r.score.bm25 <= full.results[3].score.bm25]
