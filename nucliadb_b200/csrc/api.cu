@@ -717,7 +717,8 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
         max_w = std::max<uint64_t>(max_w, wstart[ends[b]] - wstart[begin]);
     }
     int efC = s->cfg.ef_construction, M = s->cfg.m;
-    uint32_t *d_order = nullptr, *d_wpos = nullptr, *d_rev_x = nullptr, *d_idx = nullptr, *d_idx_sorted = nullptr;
+    uint32_t *d_order = nullptr, *d_wpos = nullptr, *d_rev_x = nullptr, *d_idx = nullptr, *d_idx_sorted = nullptr, *d_heads = nullptr;
+    unsigned int* d_head_ctr = nullptr;  // [0] number of heads, [1] work counter
     unsigned char* d_wlayer = nullptr;
     uint64_t *d_found = nullptr, *d_rev_key = nullptr, *d_key_sorted = nullptr;
     int* d_found_count = nullptr;
@@ -727,7 +728,7 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
     size_t max_rev = (size_t)max_w * M;
     auto cleanup = [&]() {
         cudaFree(d_order); cudaFree(d_wpos); cudaFree(d_wlayer); cudaFree(d_found); cudaFree(d_found_count); cudaFree(d_rev_key); cudaFree(d_rev_x);
-        cudaFree(d_rev_sim); cudaFree(d_key_sorted); cudaFree(d_idx); cudaFree(d_idx_sorted); cudaFree(d_cub);
+        cudaFree(d_rev_sim); cudaFree(d_key_sorted); cudaFree(d_idx); cudaFree(d_idx_sorted); cudaFree(d_cub); cudaFree(d_heads); cudaFree(d_head_ctr);
     };
     r = [&]() -> int {
         CU(cudaMalloc(&d_order, n * 4));
@@ -741,6 +742,8 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
         CU(cudaMalloc(&d_rev_sim, max_rev * 4));
         CU(cudaMalloc(&d_idx, max_rev * 4));
         CU(cudaMalloc(&d_idx_sorted, max_rev * 4));
+        CU(cudaMalloc(&d_heads, max_rev * 4));
+        CU(cudaMalloc(&d_head_ctr, 64));
         CU(cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, stream));
         CU(cudaMemcpyAsync(d_wpos, w_pos.data(), W * 4, cudaMemcpyHostToDevice, stream));
         CU(cudaMemcpyAsync(d_wlayer, w_layer.data(), W, cudaMemcpyHostToDevice, stream));
@@ -770,9 +773,19 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
         int cache_sel = (int)std::min<size_t>(M, budget / row_bytes);
         int prune_max = std::max(s->cfg.m0, M) * 95 / 100;
         int cache_rev = (int)std::min<size_t>(prune_max, budget / row_bytes);
-        size_t smem_sel = hb_smem_bytes(s->ld, cache_sel), smem_rev = hb_smem_bytes(s->ld, cache_rev);
+        // prune of a full list: stage all mmax + 1 vectors and the pairwise table when they fit (<= ~200 KB)
+        int full_rows = std::max(s->cfg.m0, M) + 1;
+        // NIDX_B200_PRUNE=table switches the prune to the staged pairwise-table variant (same result; measured
+        // slightly slower than the candidate-at-a-time loop at d = 768, M0 = 32: 4.94 s vs 4.71 s per 1M vectors)
+        const char* prune_env = getenv("NIDX_B200_PRUNE");
+        bool preload = hb_smem_bytes(s->ld, full_rows, true) <= 200 * 1024 && prune_env && !strcmp(prune_env, "table");
+        if (preload) cache_rev = full_rows;
+        size_t smem_sel = hb_smem_bytes(s->ld, cache_sel), smem_rev = hb_smem_bytes(s->ld, cache_rev, preload);
         CU(cudaFuncSetAttribute(select_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
         CU(cudaFuncSetAttribute(reverse_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rev));
+        int occ_rev = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_rev, reverse_link_kernel, HB_THREADS, smem_rev));
+        int rev_grid = std::max(1, occ_rev) * s->sm_count;
         CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
 
 
@@ -802,8 +815,12 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
             CU(cub::DeviceRadixSort::SortPairs(d_cub, tmp, d_rev_key, d_key_sorted, d_idx, d_idx_sorted, n_rev, 0, 40, stream));
             LAUNCHED();
             ReverseArgs ra;
-            ra.n_rev = n_rev; ra.key_sorted = d_key_sorted; ra.idx_sorted = d_idx_sorted; ra.rev_x = d_rev_x; ra.rev_sim = d_rev_sim; ra.cache_cap = cache_rev;
-            reverse_link_kernel<<<n_rev, HB_THREADS, smem_rev, stream>>>(V, G, ra);
+            ra.n_rev = n_rev; ra.key_sorted = d_key_sorted; ra.idx_sorted = d_idx_sorted; ra.rev_x = d_rev_x; ra.rev_sim = d_rev_sim; ra.cache_cap = cache_rev; ra.preload = preload ? 1 : 0;
+            ra.heads = d_heads; ra.n_heads = d_head_ctr; ra.work_counter = d_head_ctr + 1;
+            CU(cudaMemsetAsync(d_head_ctr, 0, 8, stream));
+            collect_heads_kernel<<<(n_rev + 255) / 256, 256, 0, stream>>>(d_key_sorted, n_rev, d_heads, d_head_ctr);
+            LAUNCHED();
+            reverse_link_kernel<<<std::min(n_rev, rev_grid), HB_THREADS, smem_rev, stream>>>(V, G, ra);
             LAUNCHED();
             begin = end;
         }

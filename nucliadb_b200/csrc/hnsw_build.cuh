@@ -19,6 +19,20 @@ namespace nidx {
 constexpr int HB_THREADS = 256;
 constexpr int HB_WARPS = HB_THREADS / 32;
 constexpr int HB_MAX_CAND = 256;  // efC <= 256 (candidates of one select), mmax + 1 <= 256
+constexpr int HB_PAIR_LD = HS_MAX_ROW + 1;  // a full adjacency row plus the pushed edge
+
+// lane-blocked dot of two rows that both live in shared memory (same arithmetic as warp_dot)
+__device__ __forceinline__ float warp_dot_ss(const float4* __restrict__ a, const float4* __restrict__ b, int ngroups, int lane) {
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+    for (int g = lane; g < ngroups; g += 32) {
+        float4 va = a[g], vb = b[g];
+        ax = __fmaf_rn(va.x, vb.x, ax);
+        ay = __fmaf_rn(va.y, vb.y, ay);
+        az = __fmaf_rn(va.z, vb.z, az);
+        aw = __fmaf_rn(va.w, vb.w, aw);
+    }
+    return butterfly_sum(__fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw)));
+}
 
 struct HeurSmem {
     uint32_t* cand_id;   // [HB_MAX_CAND]
@@ -26,14 +40,16 @@ struct HeurSmem {
     unsigned char* state;  // [HB_MAX_CAND] 0 = untouched, 1 = kept, 2 = discarded
     uint32_t* sel_id;    // [HB_MAX_CAND]
     float* sel_sim;      // [HB_MAX_CAND]
-    float* cache;        // [cache_cap][ld] kept vectors
+    float* cache;        // [cache_cap][ld] kept vectors (PRELOAD: all candidate vectors)
+    float* pair;         // PRELOAD: [HB_PAIR_LD][HB_PAIR_LD] pairwise similarities
+    unsigned char* sel_src;  // PRELOAD: candidate index of each kept entry
     int cache_cap;
     int* s_fail;
     int* s_nsel;
 };
 
-__host__ __device__ __forceinline__ size_t hb_smem_bytes(int ld, int cache_cap) {
-    return (size_t)HB_MAX_CAND * (4 + 4 + 4 + 4 + 1) + 64 + (size_t)cache_cap * ld * 4;
+__host__ __device__ __forceinline__ size_t hb_smem_bytes(int ld, int cache_cap, bool preload = false) {
+    return (size_t)HB_MAX_CAND * (4 + 4 + 4 + 4 + 1 + 1) + 64 + (size_t)cache_cap * ld * 4 + (preload ? (size_t)HB_PAIR_LD * HB_PAIR_LD * 4 : 0);
 }
 
 __device__ inline void hb_carve(HeurSmem& h, unsigned char* p, int ld, int cache_cap, int* s_ints) {
@@ -42,7 +58,9 @@ __device__ inline void hb_carve(HeurSmem& h, unsigned char* p, int ld, int cache
     h.cand_sim = reinterpret_cast<float*>(p); p += HB_MAX_CAND * 4;
     h.sel_id = reinterpret_cast<uint32_t*>(p); p += HB_MAX_CAND * 4;
     h.sel_sim = reinterpret_cast<float*>(p); p += HB_MAX_CAND * 4;
-    h.state = p;
+    h.state = p; p += HB_MAX_CAND;
+    h.sel_src = p; p += HB_MAX_CAND;
+    h.pair = reinterpret_cast<float*>(p);   // only carved when the launch reserved it (preload)
     h.cache_cap = cache_cap;
     h.s_fail = &s_ints[0];
     h.s_nsel = &s_ints[1];
@@ -50,6 +68,11 @@ __device__ inline void hb_carve(HeurSmem& h, unsigned char* p, int ld, int cache
 
 // build.rs:57-95.  Candidates (id, similarity to the new node) in h.cand_* [0, nc) in the given order.
 // Result in h.sel_* [0, return value).  All threads of the CTA call this.
+// PRELOAD (prune of a full adjacency list, nc <= mmax + 1): every candidate vector is staged in shared memory
+// once (h.cache row i = candidate i), all nc*(nc-1)/2 pairwise similarities are computed in parallel into
+// h.pair, and the sequential pick of build.rs:66-82 becomes a walk over that table by one warp -- same
+// comparisons, same result, without one HBM round trip and two barriers per candidate.
+template <bool PRELOAD>
 __device__ inline int select_neighbours_heuristic(const VecDev& V, HeurSmem& h, int nc, int k) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ng = V.ld >> 2;
@@ -57,6 +80,49 @@ __device__ inline int select_neighbours_heuristic(const VecDev& V, HeurSmem& h, 
     if (threadIdx.x == 0) *h.s_nsel = 0;
     __syncthreads();
     int nsel = 0;
+    if (PRELOAD) {
+        for (int i = warp; i < nc; i += HB_WARPS) {   // one warp per candidate row: 3 KB coalesced
+            const float4* src = reinterpret_cast<const float4*>(V.vecs + (size_t)h.cand_id[i] * V.ld);
+            float4* dst = reinterpret_cast<float4*>(h.cache + (size_t)i * V.ld);
+            for (int g = lane; g < ng; g += 32) dst[g] = ldg_stream(src + g);
+        }
+        __syncthreads();
+        int npairs = nc * (nc - 1) / 2;
+        for (int p = warp; p < npairs; p += HB_WARPS) {   // pair p = (i, j), j < i
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (i * (i - 1) / 2 > p) --i;
+            while ((i + 1) * i / 2 <= p) ++i;
+            int j = p - i * (i - 1) / 2;
+            float ab = warp_dot_ss(reinterpret_cast<const float4*>(h.cache + (size_t)i * V.ld), reinterpret_cast<const float4*>(h.cache + (size_t)j * V.ld), ng, lane);
+            if (lane == 0) {
+                float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, V.norms[h.cand_id[i]], V.norms[h.cand_id[j]]) : ab;
+                h.pair[i * HB_PAIR_LD + j] = s;
+                h.pair[j * HB_PAIR_LD + i] = s;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {   // 66-82 on the table: lanes test the kept set in parallel
+            int kept = 0;
+            for (int i = 0; i < nc && kept < k; ++i) {
+                float sim = h.cand_sim[i];
+                bool bad = false;
+                for (int j0 = 0; j0 < kept; j0 += 32) {
+                    int j = j0 + lane;
+                    bad = bad || (j < kept && !(sim > h.pair[i * HB_PAIR_LD + h.sel_src[j]]));
+                }
+                bad = __any_sync(0xFFFFFFFFu, bad);
+                if (lane == 0) {
+                    if (!bad) { h.sel_id[kept] = h.cand_id[i]; h.sel_sim[kept] = sim; h.sel_src[kept] = (unsigned char)i; h.state[i] = 1; }
+                    else h.state[i] = 2;
+                }
+                __syncwarp();
+                if (!bad) kept++;
+            }
+            if (lane == 0) *h.s_fail = kept;
+        }
+        __syncthreads();
+        nsel = *h.s_fail;
+    } else
     for (int i = 0; i < nc && nsel < k; ++i) {  // 66-69: stop once k are kept
         uint32_t x = h.cand_id[i];
         float sim = h.cand_sim[i];
@@ -145,7 +211,7 @@ __global__ void __launch_bounds__(HB_THREADS) select_link_kernel(VecDev V, Graph
     const uint64_t* f = a.found + ((size_t)slot * HS_MAX_LAYERS + layer) * a.efC;
     for (int i = threadIdx.x; i < nc; i += blockDim.x) { h.cand_id[i] = key_id(f[i]); h.cand_sim[i] = key_score(f[i]); }
     __syncthreads();
-    int nsel = select_neighbours_heuristic(V, h, nc, a.M);
+    int nsel = select_neighbours_heuristic<false>(V, h, nc, a.M);
     uint32_t* row = G.row(x, layer);
     float* wrow = G.wrow(x, layer);
     int stride = G.stride(layer);
@@ -168,43 +234,70 @@ struct ReverseArgs {
     const uint32_t* rev_x;
     const float* rev_sim;
     int cache_cap;
+    int preload;   // 1: the whole list (mmax + 1 vectors) fits in shared memory -> table-driven prune
+    const uint32_t* heads;         // compacted segment heads (indices into key_sorted)
+    const unsigned int* n_heads;
+    unsigned int* work_counter;
 };
 
-// build.rs:111-118 for one (layer, neighbour) segment per CTA.
+// Segment heads of the sorted reverse-edge records (first record of every (layer, neighbour) run), compacted so
+// that reverse_link_kernel only spends CTAs on real work.
+__global__ void collect_heads_kernel(const uint64_t* __restrict__ key_sorted, int n_rev, uint32_t* __restrict__ heads, unsigned int* __restrict__ n_heads) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool head = i < n_rev && key_sorted[i] != ~0ull && (i == 0 || key_sorted[i - 1] != key_sorted[i]);
+    unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+    if (m) {
+        int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(n_heads, (unsigned)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (head) heads[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)i;
+    }
+}
+
+// build.rs:111-118: persistent CTAs pull (layer, neighbour) segments from the compacted head list.
 __global__ void __launch_bounds__(HB_THREADS) reverse_link_kernel(VecDev V, GraphDev G, ReverseArgs a) {
-    int i0 = blockIdx.x;
-    uint64_t key = a.key_sorted[i0];
-    if (key == ~0ull) return;
-    if (i0 > 0 && a.key_sorted[i0 - 1] == key) return;  // not a segment head
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ints[4];
+    __shared__ unsigned int s_work;
     HeurSmem h;
     hb_carve(h, smem, V.ld, a.cache_cap, s_ints);
-    int layer = (int)(key >> 32);
-    uint32_t y = (uint32_t)key;
-    uint32_t* row = G.row(y, layer);
-    float* wrow = G.wrow(y, layer);
-    int stride = G.stride(layer), mmax = G.mmax(layer);
-    // current list -> sel_* (the working list lives in sel_*, candidates are staged into cand_*)
-    uint32_t mine = threadIdx.x < stride ? row[threadIdx.x] : NIL;  // rows are prefix-filled, stride <= 64
-    if (mine != NIL) { h.sel_id[threadIdx.x] = mine; h.sel_sim[threadIdx.x] = wrow[threadIdx.x]; }
-    int len = __syncthreads_count(mine != NIL);
-    for (int i = i0; i < a.n_rev && a.key_sorted[i] == key; ++i) {
-        uint32_t src = a.idx_sorted[i];
+    const unsigned int n_heads = *a.n_heads;
+    while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) { h.sel_id[len] = a.rev_x[src]; h.sel_sim[len] = a.rev_sim[src]; }  // other_edges.push((x, dist))
-        len++;
+        if (threadIdx.x == 0) s_work = atomicAdd(a.work_counter, 1u);
         __syncthreads();
-        if (len > mmax) {  // 115-117
-            for (int j = threadIdx.x; j < len; j += blockDim.x) { h.cand_id[j] = h.sel_id[j]; h.cand_sim[j] = h.sel_sim[j]; }
+        unsigned int wi = s_work;
+        if (wi >= n_heads) break;
+        int i0 = (int)a.heads[wi];
+        uint64_t key = a.key_sorted[i0];
+        int layer = (int)(key >> 32);
+        uint32_t y = (uint32_t)key;
+        uint32_t* row = G.row(y, layer);
+        float* wrow = G.wrow(y, layer);
+        int stride = G.stride(layer), mmax = G.mmax(layer);
+        // current list -> sel_* (the working list lives in sel_*, candidates are staged into cand_*)
+        uint32_t mine = threadIdx.x < stride ? row[threadIdx.x] : NIL;  // rows are prefix-filled, stride <= 64
+        if (mine != NIL) { h.sel_id[threadIdx.x] = mine; h.sel_sim[threadIdx.x] = wrow[threadIdx.x]; }
+        int len = __syncthreads_count(mine != NIL);
+        for (int i = i0; i < a.n_rev && a.key_sorted[i] == key; ++i) {
+            uint32_t src = a.idx_sorted[i];
             __syncthreads();
-            len = select_neighbours_heuristic(V, h, len, mmax * 95 / 100);  // params.rs:29-31 prune_m
+            if (threadIdx.x == 0) { h.sel_id[len] = a.rev_x[src]; h.sel_sim[len] = a.rev_sim[src]; }  // other_edges.push((x, dist))
+            len++;
+            __syncthreads();
+            if (len > mmax) {  // 115-117
+                for (int j = threadIdx.x; j < len; j += blockDim.x) { h.cand_id[j] = h.sel_id[j]; h.cand_sim[j] = h.sel_sim[j]; }
+                __syncthreads();
+                len = a.preload ? select_neighbours_heuristic<true>(V, h, len, mmax * 95 / 100)   // params.rs:29-31 prune_m
+                                : select_neighbours_heuristic<false>(V, h, len, mmax * 95 / 100);
+            }
         }
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < stride; j += blockDim.x) {
-        row[j] = j < len ? h.sel_id[j] : NIL;
-        wrow[j] = j < len ? h.sel_sim[j] : 0.0f;
+        __syncthreads();
+        for (int j = threadIdx.x; j < stride; j += blockDim.x) {
+            row[j] = j < len ? h.sel_id[j] : NIL;
+            wrow[j] = j < len ? h.sel_sim[j] : 0.0f;
+        }
     }
 }
 

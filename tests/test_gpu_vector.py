@@ -203,3 +203,36 @@ def test_search_is_reentrant(small_data):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 33])
+def test_tiny_segments(n):
+    """Edge cases the reference tests exercise: empty segment, one node (hnsw_deserialize_one_node), fewer nodes than M."""
+    d = 16
+    v = make_vectors(max(n, 1), d, seed=40 + n)[:n]
+    q = make_queries(make_vectors(8, d, seed=2), 4)
+    seg = VectorSegment.create(v if n else np.zeros((0, d), np.float32), d, similarity=_lib.NIDX_SIM_COSINE, m=4, m0=8, ef_construction=16)
+    ids, sc, cnt = seg.search(q, 5, method=_lib.NIDX_METHOD_BRUTE)
+    if n == 0:
+        assert (cnt == 0).all() and (ids == 0xFFFFFFFF).all()
+        return
+    oi, os_, oc = O.brute_force(v, q, 5)
+    assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+    seg.build_hnsw(seed=2, max_batch=4)
+    g = seg.get_graph()
+    og = O.hnsw_build(v, M=4, M0=8, efC=16, seed=2, max_batch=4)
+    assert (g["adj0"] == og.adj0).all() and (g["level"] == og.level).all()
+    hi, hs, hc = seg.search(q, 5, ef=8, method=_lib.NIDX_METHOD_HNSW)
+    gi, gs, gc, _ = O.hnsw_search(v, og, q, 5, 8)
+    assert (hc == gc).all() and (hi == gi).all() and np.array_equal(hs, gs)
+
+
+@pytest.mark.parametrize("prune", ["table", "seq"])
+def test_prune_variants_build_the_same_graph(prune, monkeypatch):
+    monkeypatch.setenv("NIDX_B200_PRUNE", prune)
+    v = make_vectors(3000, 64, seed=14)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=8, m0=16, ef_construction=40)
+    seg.build_hnsw(seed=2, max_batch=128)
+    g = seg.get_graph()
+    og = O.hnsw_build(v, M=8, M0=16, efC=40, seed=2, max_batch=128, nthreads=8)
+    assert (g["adj0"] == og.adj0).all() and np.array_equal(g["w0"], og.w0)
