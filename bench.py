@@ -288,6 +288,19 @@ def main():
     torch.cuda.synchronize()
     ids_np = ids.cpu().numpy()
     recall = recall_at_k(ids_np, gt)
+    # the reference's compile-time operating point (params.rs:46 EF_SEARCH = 30) on the same graph, for context
+    ef30 = None
+    if not multi:
+        i30, _, _ = seg.search(queries[args.warmup], k, ef=30, method=_lib.NIDX_METHOD_HNSW)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.warmup, min(n_batches, args.warmup + 5)):
+            seg.search(queries[i], k, ef=30, method=_lib.NIDX_METHOD_HNSW, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        n30 = min(n_batches, args.warmup + 5) - args.warmup
+        ef30 = {"recall_at_10": recall_at_k(i30.cpu().numpy(), gt), "qps": nq * n30 / (e0.elapsed_time(e1) * 1e-3)}
     kernel_ms, alg_bytes = [], []
     ld = (d + 3) // 4 * 4
     for i in range(args.warmup, min(n_batches, args.warmup + 8)):
@@ -370,6 +383,7 @@ def main():
                        "data_gen": f"latent={args.latent} noise={args.noise} normalised; queries = data point + 0.05 * unit noise"},
             "merged_qps": nq * args.steps / (ms_total * 1e-3),
             "recall_at_10": recall,
+            "ef30": ef30,
             "build": {"seconds": t_build, "vectors_per_s": n / t_build, "similarities": build_counters["similarities"], "max_batch": args.max_batch,
                       "data_seconds": t_data},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

@@ -75,14 +75,55 @@ def bench_scan(args):
         cpu_dt = time.perf_counter() - t0
         pk = float(peaks().get("hbm_gbs", 6650.0))
         ach = alg / (kms * 1e-3) / 1e9
+        if qq.shape[0] >= 128:   # tensor-core path: 3 TF32 MMAs per product; TF32 dense peak = half the measured bf16 peak
+            tf = 3 * 2.0 * n * d * qq.shape[0] / (kms * 1e-3) / 1e12
+            tpk = float(peaks().get("bf16_tflops", 1590.0)) / 2
+            roof = {"bound": "tensor", "achieved": tf, "peak": tpk, "unit": "TFLOP/s", "frac": tf / tpk, "kernel": "scan_scores_tc_kernel", "kernel_ms": kms,
+                    "traffic": None, "note": "3xTF32 MMA flops; peak = MEASURED_PEAKS bf16_tflops / 2 (TF32 runs at half the bf16 rate)"}
+        else:
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "scan_scores_kernel_t", "kernel_ms": kms, "traffic": None}
         lines.append({"metric": "exact k-NN QPS (brute force)", "value": qq.shape[0] / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": f"nidx_vector brute-force cosine top-10, {n}x{d} f32, {label}", "passes_over_block": passes},
                       "parity": {"ids_identical_to_oracle": bool((ids == oi).all()), "max_abs_score_diff": float(np.abs(sc - os_).max())},
-                      "roofline": {"bound": "hbm" if qq.shape[0] == 1 else "fma/shared (the block is re-read per 8-query tile from L2)", "achieved": ach, "peak": pk,
-                                   "unit": "GB/s", "frac": ach / pk, "kernel": "scan_scores_kernel", "kernel_ms": kms, "traffic": None},
+                      "roofline": roof,
                       "cpu_baseline": {"value": min(qq.shape[0], 256) / cpu_dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                                        "sample": f"{min(qq.shape[0], 256)} queries"}})
+    return lines
+
+
+def bench_build(args):
+    """configs[2]: HNSW index build (per 1M x 768 here; bench.py reports the 10M build of the headline run) at the
+    BASELINE constants (M=16, efC=200) and at the reference's compile-time constants (M=30/60, efC=100)."""
+    import torch
+
+    from bench import gen_queries, gen_vectors, recall_at_k
+    from nucliadb_b200 import _lib
+    from nucliadb_b200.segment import VectorSegment
+
+    dev = torch.device("cuda", 0)
+    n, d = args.build_vectors, 768
+    vecs = gen_vectors(n, d, dev, seed=1234567890, latent=16, noise=0.15)
+    q = gen_queries(vecs, 1024, seed=123)
+    lines = []
+    for m, m0, efc in ((16, 32, 200), (30, 60, 100)):
+        seg = VectorSegment.create(vecs, d, similarity=_lib.NIDX_SIM_COSINE, m=m, m0=m0, ef_construction=efc)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        seg.build_hnsw(seed=2, max_batch=8192)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        c = seg.counters()
+        gt = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)[0].cpu().numpy()
+        rec = {ef: recall_at_k(seg.search(q, 10, ef=ef, method=_lib.NIDX_METHOD_HNSW)[0].cpu().numpy(), gt) for ef in (30, 128)}
+        alg = c["similarities"] * (d * 4 + 4)
+        pk = float(peaks().get("hbm_gbs", 6650.0))
+        lines.append({"metric": "HNSW build vectors/s", "value": n / dt, "unit": "vectors/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"HNSW index build {n}x{d}, M={m} M0={m0} efC={efc}", "max_batch": 8192}, "seconds": dt,
+                      "similarities": c["similarities"], "visited_overflows": c["overflows"], "recall_at_10": rec,
+                      "roofline": {"bound": "hbm", "achieved": alg / dt / 1e9, "peak": pk, "unit": "GB/s", "frac": alg / dt / 1e9 / pk,
+                                   "note": "whole build (search + select + reverse-link + sort) over the search kernel's algorithmic bytes"}})
+        seg.close()
     return lines
 
 
@@ -184,7 +225,8 @@ def bench_bm25(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["scan", "bm25", "all"])
+    ap.add_argument("which", choices=["scan", "bm25", "build", "all"])
+    ap.add_argument("--build-vectors", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--docs", type=int, default=5_000_000)
@@ -194,6 +236,8 @@ def main():
         lines += bench_scan(args)
     if args.which in ("bm25", "all"):
         lines += bench_bm25(args)
+    if args.which in ("build", "all"):
+        lines += bench_build(args)
     for line in lines:
         print(json.dumps(line))
 
