@@ -22,6 +22,8 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+from bench import effective_cores  # noqa: E402
+
 
 def peaks():
     try:
@@ -69,9 +71,9 @@ def bench_scan(args):
         alg = n * d * 4                                        # algorithmic bytes: the block once per launch
         ids = o[0].cpu().numpy().astype(np.uint32)
         sc = o[1].cpu().numpy()
-        oi, os_, _ = O.brute_force(host_v, host_q[: qq.shape[0]], k, nthreads=os.cpu_count())
+        oi, os_, _ = O.brute_force(host_v, host_q[: qq.shape[0]], k, nthreads=effective_cores())
         t0 = time.perf_counter()
-        O.brute_force(host_v, host_q[: min(qq.shape[0], 256)], k, nthreads=os.cpu_count())
+        O.brute_force(host_v, host_q[: min(qq.shape[0], 256)], k, nthreads=effective_cores())
         cpu_dt = time.perf_counter() - t0
         pk = float(peaks().get("hbm_gbs", 6650.0))
         ach = alg / (kms * 1e-3) / 1e9
@@ -87,7 +89,7 @@ def bench_scan(args):
                       "config": {"workload": f"nidx_vector brute-force cosine top-10, {n}x{d} f32, {label}", "passes_over_block": passes},
                       "parity": {"ids_identical_to_oracle": bool((ids == oi).all()), "max_abs_score_diff": float(np.abs(sc - os_).max())},
                       "roofline": roof,
-                      "cpu_baseline": {"value": min(qq.shape[0], 256) / cpu_dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                      "cpu_baseline": {"value": min(qq.shape[0], 256) / cpu_dt, "unit": "queries/s", "cores": effective_cores(), "kind": "port",
                                        "sample": f"{min(qq.shape[0], 256)} queries"}})
     return lines
 
@@ -205,7 +207,7 @@ def bench_bm25(args):
         # oracle on a bounded sample
         ns = 64
         t0 = time.perf_counter()
-        od, osc, oc, otot = O.bm25_search(P, [list(x) for x in queries[:ns]], k, mode=mode, use_tf=use_tf, nthreads=os.cpu_count())
+        od, osc, oc, otot = O.bm25_search(P, [list(x) for x in queries[:ns]], k, mode=mode, use_tf=use_tf, nthreads=effective_cores())
         cpu_dt = time.perf_counter() - t0
         ok_counts = bool((cnt[:ns] == oc).all() and (tot[:ns] == otot).all())
         rel = float(np.max(np.abs(sc[:ns] - osc) / np.maximum(1.0, np.abs(osc))))
@@ -218,7 +220,7 @@ def bench_bm25(args):
                                  "postings_per_query": postings / nq, "setup_seconds": t_setup},
                       "parity": {"counts_identical_to_oracle": ok_counts, "max_rel_score_diff": rel, "ids_identical_fraction": same_ids, "sample": ns},
                       "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "bm25_kernel", "kernel_ms": ms, "traffic": None},
-                      "cpu_baseline": {"value": ns / cpu_dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"{ns} queries"},
+                      "cpu_baseline": {"value": ns / cpu_dt, "unit": "queries/s", "cores": effective_cores(), "kind": "port", "sample": f"{ns} queries"},
                       "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(qt_h.nbytes + qo_h.nbytes), "d2h_bytes_per_step": nq * k * 8 + nq * 12}})
     return lines
 
