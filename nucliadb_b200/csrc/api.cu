@@ -1096,8 +1096,18 @@ int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint
     a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.mode = p->mode; a.use_tf = p->use_tf; a.k = k; a.cap = cap;
     a.term_weight = t->d_weight; a.norm_cache = t->d_norm_cache; a.shift = shift;
     a.after_mode = p->after_mode; a.after_score = p->after_score; a.after_docaddr = p->after_docaddr; a.docaddr_base = p->docaddr_base; a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total;
-    CU(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bm25_kernel<<<nq, BM_THREADS, smem, stream>>>(T, a);
+    // NIDX_B200_BM25=tm selects the term-major variant (warp per term slice, no scan / search, two barriers per tile).
+    // Measured SLOWER than the flattened kernel on the 5M-doc / 50-term workload (97k vs 169k QPS: 12-posting slices
+    // leave 60 % of the lanes idle and serialise a warp's terms), so it stays an experiment.
+    const char* bm_env = getenv("NIDX_B200_BM25");
+    if (max_terms <= BM_TM_TERMS && bm_env && !strcmp(bm_env, "tm")) {
+        size_t smem_tm = bm_tm_smem_bytes(cap, p->mode == NIDX_BM25_AND);
+        CU(cudaFuncSetAttribute(bm25_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm));
+        bm25_tm_kernel<<<nq, BM_THREADS, smem_tm, stream>>>(T, a);
+    } else {
+        CU(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bm25_kernel<<<nq, BM_THREADS, smem, stream>>>(T, a);
+    }
     LAUNCHED();
     bm25_finish_kernel<<<nq, 128, 0, stream>>>(w.partial.as<uint64_t>(), nq, k, p->min_score, d_docs, d_sc, d_cnt);
     LAUNCHED();

@@ -301,6 +301,174 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_kernel(TxtDev T, Bm25Args a) 
     if (threadIdx.x == 0 && a.out_total) a.out_total[q] = s_hits;
 }
 
+// ---- term-major variant (queries with at most BM_TM_TERMS terms) ---------------------------------------------
+// The flattened kernel above spends most of its instructions on bookkeeping that exists only to balance postings
+// over threads (per-tile prefix scan, a binary search per posting and pass, four barriers per tile).  With ~12
+// postings per (term, tile) a warp per term slice is balanced enough, and everything about a term -- cursor, skip
+// prefetch, weight -- can live in the registers of ONE lane of the warp that owns it (term t belongs to warp
+// t % 8, lane t / 8), broadcast by shuffle when the slice is processed: no shared-memory cursor arrays, no scan,
+// no search, two barriers per tile (accumulate | collect).
+constexpr int BM_TM_OWN = 8;                         // terms per warp
+constexpr int BM_TM_TERMS = BM_TM_OWN * (BM_THREADS / 32);
+
+__host__ __device__ __forceinline__ size_t bm_tm_smem_bytes(int cap, bool conj) {
+    return (size_t)BM_TILE * 4 + (conj ? (size_t)BM_TILE : 0) + (size_t)cap * 8 + (size_t)BM_TOUCH_CAP * 2 + 1024 + 64;
+}
+
+__global__ void __launch_bounds__(BM_THREADS) bm25_tm_kernel(TxtDev T, Bm25Args a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int tk_count;
+    __shared__ uint64_t tk_thr;
+    __shared__ int s_ntouched[2];
+    __shared__ unsigned long long s_hits;
+    unsigned char* p = smem;
+    uint64_t* tk_buf = reinterpret_cast<uint64_t*>(p); p += (size_t)a.cap * 8;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(p); p += (size_t)BM_TILE * 4;
+    float* ncache = reinterpret_cast<float*>(p); p += 1024;
+    unsigned short* touched = reinterpret_cast<unsigned short*>(p); p += (size_t)BM_TOUCH_CAP * 2;
+    unsigned char* cnt8 = p;   // [BM_TILE] matched-term counters (AND only)
+
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t* terms = a.query_terms + a.query_off[q];
+    int nt = (int)(a.query_off[q + 1] - a.query_off[q]);
+    if (nt > BM_TM_TERMS) nt = BM_TM_TERMS;
+    BlockTopK tk;
+    tk.init(tk_buf, &tk_count, &tk_thr, a.k, a.cap);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) ncache[i] = a.norm_cache[i];
+    for (int i = threadIdx.x; i < BM_TILE; i += blockDim.x) acc[i] = 0;
+    if (a.mode == 1) for (int i = threadIdx.x; i < BM_TILE / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(cnt8)[i] = 0;
+
+    // this lane's term (if any): t = warp + 8 * lane
+    const int my_t = warp + (BM_THREADS / 32) * lane;
+    const bool own = lane < BM_TM_OWN && my_t < nt;
+    const int n_own = nt > warp ? (nt - warp + (BM_THREADS / 32) - 1) / (BM_THREADS / 32) : 0;   // terms owned by this warp (warp-uniform)
+    uint64_t t_base = 0, t_end = 0, t_next = 0;
+    size_t t_skip = 0;
+    uint32_t pf_end = 0;
+    bool has_skip = false;
+    float t_w = 0.0f;
+    bool missing = false;
+    if (own) {
+        uint32_t t = terms[my_t];
+        bool ok = t < T.n_terms;
+        t_base = ok ? T.term_off[t] : 0;
+        t_end = ok ? T.term_off[t + 1] : 0;
+        t_w = ok ? a.term_weight[t] : 0.0f;
+        uint32_t row = ok ? T.skip_row[t] : NIL;
+        has_skip = row != NIL;
+        missing = t_base == t_end;
+        t_next = t_base;
+        if (has_skip) { t_skip = (size_t)row * (T.n_tiles + 1); pf_end = T.skip[t_skip + 1]; }
+    }
+    if (threadIdx.x == 0) { s_hits = 0; s_ntouched[0] = 0; s_ntouched[1] = 0; }
+    int any_missing = __syncthreads_or(missing);
+    const bool dead = (a.mode == 1 && any_missing) || nt == 0;
+    const float scale = (float)(1u << a.shift);
+    const uint32_t n_tiles = dead ? 0 : T.n_tiles;
+    unsigned int my_hits = 0;
+
+    for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        const int cb = tile & 1;
+        const uint32_t lo = tile * BM_TILE;
+        const uint32_t hi = lo + BM_TILE < T.n_docs ? lo + BM_TILE : T.n_docs;
+        // slice [sb, se) of this lane's term in the tile
+        uint64_t sb = t_next, se = t_next;
+        if (own) {
+            if (has_skip) {
+                se = t_base + pf_end;
+                if (tile + 2 <= T.n_tiles) pf_end = T.skip[t_skip + tile + 2];
+            } else {
+                while (se < t_end && T.post_doc[se] < hi) ++se;
+            }
+            t_next = se;
+        }
+        bool do_tile = true;
+        if (a.mode == 1) do_tile = __syncthreads_and(!own || se > sb);   // AND: some term has nothing in this tile
+        if (do_tile) {
+            // pass 1: first chunk of every owned term loaded up front (independent loads in flight), then accumulated
+            uint32_t d0[BM_TM_OWN], f0[BM_TM_OWN];
+#pragma unroll
+            for (int j = 0; j < BM_TM_OWN; ++j) {
+                uint64_t b = __shfl_sync(0xFFFFFFFFu, sb, j), e = __shfl_sync(0xFFFFFFFFu, se, j);
+                d0[j] = 0; f0[j] = 0;
+                if (j < n_own && b + lane < e) { d0[j] = __ldg(T.post_doc + b + lane); f0[j] = __ldg(T.post_tfn + b + lane); }
+            }
+#pragma unroll
+            for (int j = 0; j < BM_TM_OWN; ++j) {
+                if (j >= n_own) break;
+                uint64_t b = __shfl_sync(0xFFFFFFFFu, sb, j), e = __shfl_sync(0xFFFFFFFFu, se, j);
+                float w = __shfl_sync(0xFFFFFFFFu, t_w, j);
+                for (uint64_t base = b; base < e; base += 32) {   // warp-uniform trip count
+                    bool act = base + lane < e;
+                    uint32_t d = d0[j], tfn = f0[j];
+                    if (base != b && act) { d = __ldg(T.post_doc + base + lane); tfn = __ldg(T.post_tfn + base + lane); }
+                    bool first = false;
+                    uint32_t off = 0;
+                    if (act) {
+                        float tff = a.use_tf ? (float)(tfn >> 8) : 1.0f;
+                        float sc = __fmul_rn(w, __fdiv_rn(tff, __fadd_rn(tff, ncache[tfn & 0xFFu])));
+                        uint32_t fx = (uint32_t)__float2uint_rn(__fmul_rn(sc, scale));
+                        if (fx == 0) fx = 1;
+                        off = d - lo;
+                        first = atomicAdd(&acc[off], fx) == 0;
+                        if (a.mode == 1) atomicAdd(reinterpret_cast<uint32_t*>(cnt8) + (off >> 2), 1u << (8 * (off & 3)));
+                    }
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, first);
+                    if (m) {
+                        int basepos = 0;
+                        if (lane == 0) basepos = atomicAdd(&s_ntouched[cb], __popc(m));
+                        basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+                        int pos = basepos + __popc(m & ((1u << lane) - 1));
+                        if (first && pos < BM_TOUCH_CAP) touched[pos] = (unsigned short)off;
+                    }
+                }
+            }
+            __syncthreads();
+            // pass 2: every touched document once
+            int ntouched = s_ntouched[cb];
+            bool dense = ntouched > BM_TOUCH_CAP;
+            int work = dense ? (int)(hi - lo) : ntouched;
+            for (int base = 0; base < work; base += BM_THREADS * BM_ROUND) {
+#pragma unroll
+                for (int u = 0; u < BM_ROUND; ++u) {
+                    int j = base + u * BM_THREADS + threadIdx.x;
+                    if (j < work) {
+                        uint32_t off = dense ? (uint32_t)j : (uint32_t)touched[j];
+                        uint32_t v = acc[off];
+                        if (v != 0) {
+                            acc[off] = 0;
+                            bool match = true;
+                            if (a.mode == 1) { match = (int)cnt8[off] == nt; cnt8[off] = 0; }
+                            uint32_t doc = lo + off;
+                            if (match && T.alive) match = (T.alive[doc >> 6] >> (doc & 63)) & 1;
+                            if (match) {
+                                my_hits++;
+                                float score = __fdiv_rn((float)v, scale);
+                                bool after = true;
+                                if (a.after_mode != 0) {
+                                    uint32_t so = ordered_bits(score), ao = ordered_bits(a.after_score);
+                                    after = so < ao || (so == ao && (a.after_mode == 3 || (a.after_mode == 2 && a.docaddr_base + doc > a.after_docaddr)));
+                                }
+                                uint64_t key = make_key(score, doc, 0);
+                                if (after && key > tk_thr) tk_buf[atomicAdd(&tk_count, 1)] = key;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tk_count > a.cap - BM_THREADS * BM_ROUND) tk.flush();
+            }
+            if (threadIdx.x == 0 && ntouched > 0) s_ntouched[cb] = 0;   // next user of this parity: tile + 2, behind tile + 1's barrier
+        }
+    }
+    for (int off = 16; off >= 1; off >>= 1) my_hits += __shfl_xor_sync(0xFFFFFFFFu, my_hits, off);
+    if (lane == 0 && my_hits) atomicAdd(&s_hits, (unsigned long long)my_hits);
+    int c = tk.finish();
+    uint64_t* out = a.out_keys + (size_t)q * a.k;
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) out[i] = i < c ? tk_buf[i] : 0;
+    if (threadIdx.x == 0 && a.out_total) a.out_total[q] = s_hits;
+}
+
 // keys -> (doc, score, count) with the min_score cut applied after top-k (reader.rs:302-305).
 __global__ void bm25_finish_kernel(const uint64_t* keys, int nq, int k, float min_score, uint32_t* out_docs, float* out_scores, int* out_counts) {
     int q = blockIdx.x;

@@ -87,3 +87,18 @@ def test_bm25_min_score_alive_and_missing_terms():
     d3, s3, c3, _ = run(P, [[5, 6, 7]], 20, _lib.NIDX_BM25_OR, True, min_score=thr)
     assert c3[0] == int((s0[0, : c0[0]] >= thr).sum()) and (s3[0, : c3[0]] >= thr).all()
     assert (d3[0, : c3[0]] == d0[0, : c3[0]]).all()
+
+
+def test_bm25_term_major_variant_matches(monkeypatch):
+    """The experimental term-major kernel (NIDX_B200_BM25=tm) must give the same answers as the default one."""
+    P = corpus(40000, 3000, seed=17)
+    rng = np.random.default_rng(2)
+    queries = [list(rng.choice(300, 10, replace=False) + 10) for _ in range(24)]
+    base = run(P, queries, 50, _lib.NIDX_BM25_OR, True)
+    monkeypatch.setenv("NIDX_B200_BM25", "tm")
+    tm = run(P, queries, 50, _lib.NIDX_BM25_OR, True)
+    assert (base[0] == tm[0]).all() and np.array_equal(base[1], tm[1]) and (base[2] == tm[2]).all() and (base[3] == tm[3]).all()
+    tm_and = run(P, [q[:3] for q in queries], 50, _lib.NIDX_BM25_AND, True)
+    monkeypatch.delenv("NIDX_B200_BM25")
+    base_and = run(P, [q[:3] for q in queries], 50, _lib.NIDX_BM25_AND, True)
+    assert (base_and[0] == tm_and[0]).all() and np.array_equal(base_and[1], tm_and[1]) and (base_and[3] == tm_and[3]).all()
