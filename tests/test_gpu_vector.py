@@ -236,3 +236,49 @@ def test_prune_variants_build_the_same_graph(prune, monkeypatch):
     g = seg.get_graph()
     og = O.hnsw_build(v, M=8, M0=16, efC=40, seed=2, max_batch=128, nthreads=8)
     assert (g["adj0"] == og.adj0).all() and np.array_equal(g["w0"], og.w0)
+
+
+def test_zero_vectors_and_large_k(small_data):
+    """simsimd's cosine edge cases (both norms 0 -> similarity 1, ab == 0 -> 0) and k close to ef."""
+    v, q = small_data
+    v = v.copy()
+    v[7] = 0.0
+    qq = np.concatenate([q[:6], np.zeros((1, v.shape[1]), np.float32)])
+    g = O.hnsw_build(v, M=16, M0=32, efC=100, max_batch=64, nthreads=8)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=100)
+    seg.set_graph(g.level, g.adj0, g.adjU)
+    for k, ef in ((100, 128), (128, 30), (1, 1)):
+        bi, bs, bc = seg.search(qq, k, method=_lib.NIDX_METHOD_BRUTE)
+        oi, os_, oc = O.brute_force(v, qq, k, nthreads=4)
+        assert (bc == oc).all() and (bi == oi).all() and np.array_equal(bs, os_)
+        hi, hs, hc = seg.search(qq, k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+        gi, gs, gc, _ = O.hnsw_search(v, g, qq, k, ef, nthreads=4)
+        # the all-zero query scores every vector exactly 0 (one big tie): graph walks under exact ties are
+        # unspecified in the reference (BinaryHeap order), so only its counts are compared
+        assert (hc == gc).all() and (hi[:6] == gi[:6]).all() and np.array_equal(hs[:6], gs[:6])
+        assert seg.counters()["overflows"] == 0
+    assert bs[6, 0] == 1.0 and bi[6, 0] == 7      # zero query vs the zero vector: distance 0
+
+
+def test_multi_vector_paragraphs_match_oracle():
+    """VectorCardinality::Multi: brute force takes the best vector per paragraph (segment.rs:581-592), the HNSW walk
+    keeps one vector per paragraph (NodeFilter.paragraphs, search.rs:159-165)."""
+    rng = np.random.default_rng(9)
+    n_par = 3000
+    num = rng.integers(1, 5, n_par).astype(np.uint32)
+    first = np.concatenate([[0], np.cumsum(num)[:-1]]).astype(np.uint32)
+    n = int(num.sum())
+    v = make_vectors(n, 64, seed=19)
+    par_of = np.repeat(np.arange(n_par, dtype=np.uint32), num)
+    q = make_queries(v, 24)
+    seg = VectorSegment.create(v, 64, similarity=_lib.NIDX_SIM_DOT, m=8, m0=16, ef_construction=40, multi_vector=True, paragraph_of=par_of)
+    ids, sc, cnt = seg.search(q, 10, min_score=0.0, method=_lib.NIDX_METHOD_BRUTE)
+    oi, os_, oc = O.brute_force(v, q, 10, sim=O.SIM_DOT, min_score=0.0, first_vec=first, num_vec=num)
+    assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+    assert all(len(set(par_of[r[:c]])) == c for r, c in zip(ids, cnt))
+    g = O.hnsw_build(v, sim=O.SIM_DOT, M=8, M0=16, efC=40, max_batch=64, nthreads=8)
+    seg.set_graph(g.level, g.adj0, g.adjU)
+    hi, hs, hc = seg.search(q, 10, ef=40, min_score=0.0, with_duplicates=True, method=_lib.NIDX_METHOD_HNSW)
+    gi, gs, gc, _ = O.hnsw_search(v, g, q, 10, 40, sim=O.SIM_DOT, min_score=0.0, with_duplicates=True, multi_vector=True, paragraph_of=par_of, nthreads=4)
+    assert (hc == gc).all() and (hi == gi).all() and np.array_equal(hs, gs)
+    assert all(len(set(par_of[r[:c]])) == c for r, c in zip(hi, hc))
