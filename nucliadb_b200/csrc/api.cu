@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "hnsw_build.cuh"
 #include "hnsw_search.cuh"
+#include "rabitq.cuh"
 #include "scan.cu"
 #include "scan_tc.cuh"
 #include "segment_io.hpp"
@@ -132,6 +133,8 @@ struct nidx_vec_segment {
     uint32_t* d_adj0 = nullptr; float* d_w0 = nullptr;
     uint64_t* d_upper_off = nullptr;
     uint32_t* d_adjU = nullptr; float* d_wU = nullptr;
+    unsigned char* d_quant = nullptr;   // RaBitQ codes [n][quant_stride] (vectors.quant records, padded)
+    int quant_stride = 0;
     unsigned long long* d_counters = nullptr;  // [4]
     unsigned int* d_work_counter = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the dominant kernel of the last search (bench roofline)
@@ -324,7 +327,7 @@ void nidx_vec_close(nidx_vec_segment* s) {
     cudaDeviceSynchronize();
     free_graph(s);
     cudaFree(s->d_vecs); cudaFree(s->d_norms); cudaFree(s->d_par_of); cudaFree(s->d_par_first); cudaFree(s->d_alive);
-    cudaFree(s->d_counters); cudaFree(s->d_work_counter);
+    cudaFree(s->d_counters); cudaFree(s->d_work_counter); cudaFree(s->d_quant);
     if (s->ev_k0) cudaEventDestroy(s->ev_k0);
     if (s->ev_k1) cudaEventDestroy(s->ev_k1);
     delete s;
@@ -394,6 +397,96 @@ int nidx_vec_counters(nidx_vec_segment* s, uint64_t out[3]) {
     unsigned long long h[4];
     CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2] + h[3];
+    return 0;
+}
+
+// ---- RaBitQ --------------------------------------------------------------------------------------
+static int rabitq_check(const nidx_vec_segment* s) {
+    if (s->cfg.similarity != NIDX_SIM_DOT || s->d % 64 != 0) return fail(NIDX_EINVAL, "RaBitQ needs Dot similarity and dimension %% 64 == 0 (config.rs:170-173)");
+    if (s->d / 32 > RQ_MAX_WORDS32) return fail(NIDX_EINVAL, "RaBitQ: dimension above %d not supported", RQ_MAX_WORDS32 * 32);
+    return 0;
+}
+
+int nidx_vec_rabitq_encode(nidx_vec_segment* s, void* stream_) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    int r = rabitq_check(s);
+    if (r) return r;
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    s->quant_stride = rabitq_stride(s->d);
+    if (!s->d_quant) CU(cudaMalloc(&s->d_quant, std::max<size_t>((size_t)s->n * s->quant_stride, 16)));
+    if (s->n) {
+        rabitq_encode_kernel<<<(unsigned)((s->n + 7) / 8), 256, 0, stream>>>(s->vdev(), s->d_quant, s->quant_stride);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int nidx_vec_rabitq_codes(const nidx_vec_segment* s, uint8_t* out) {
+    if (!s || !out) return fail(NIDX_EINVAL, "null argument");
+    if (!s->d_quant) return fail(NIDX_ESTATE, "segment has no RaBitQ codes (call nidx_vec_rabitq_encode)");
+    CU(cudaSetDevice(s->cfg.device));
+    size_t rec = (size_t)s->d / 8 + 8;
+    CU(cudaMemcpy2D(out, rec, s->d_quant, (size_t)s->quant_stride, rec, (size_t)s->n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// queries -> padded device copy + RaBitQ planes/params in the workspace; returns device pointers
+static int rabitq_prepare_queries(nidx_vec_segment* s, Workspace& w, const float* queries, int nq, int ldq, bool host, cudaStream_t stream, float** dq_out,
+                                  uint32_t** planes_out, RabitqQueryParams** params_out) {
+    ENSURE(w.queries, (size_t)nq * s->ld * 4);
+    float* dq = w.queries.as<float>();
+    if (ldq == s->ld) {
+        CU(cudaMemcpyAsync(dq, queries, (size_t)nq * ldq * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+    } else {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(queries);
+        if (host) {
+            ENSURE(w.misc, (size_t)nq * ldq * 4);
+            CU(cudaMemcpyAsync(w.misc.p, queries, (size_t)nq * ldq * 4, cudaMemcpyHostToDevice, stream));
+            src = w.misc.as<unsigned char>();
+        }
+        pad_rows_kernel<<<std::min(nq, 1024), 256, 0, stream>>>(src, (size_t)ldq * 4, s->d, dq, s->ld, (uint64_t)nq);
+        LAUNCHED();
+    }
+    size_t plane_bytes = (size_t)nq * 4 * (s->d / 32) * 4;
+    ENSURE(w.qnorms, plane_bytes + (size_t)nq * sizeof(RabitqQueryParams) + 64);
+    uint32_t* planes = w.qnorms.as<uint32_t>();
+    RabitqQueryParams* params = reinterpret_cast<RabitqQueryParams*>(w.qnorms.as<unsigned char>() + ((plane_bytes + 15) / 16) * 16);
+    rabitq_query_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(dq, s->ld, s->d, nq, planes, params);
+    LAUNCHED();
+    *dq_out = dq; *planes_out = planes; *params_out = params;
+    return 0;
+}
+
+int nidx_vec_rabitq_estimate(nidx_vec_segment* s, const float* queries, int32_t nq, int32_t ldq, int mem, float* out_est, float* out_err, void* stream_) {
+    if (!s || !queries || !out_est || !out_err || nq <= 0) return fail(NIDX_EINVAL, "bad argument");
+    if (!s->d_quant) return fail(NIDX_ESTATE, "segment has no RaBitQ codes (call nidx_vec_rabitq_encode)");
+    if (ldq < s->d) return fail(NIDX_EINVAL, "query dimension %d != index dimension %d", ldq, s->d);
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    WsGuard g(s->pool, stream);
+    Workspace& w = *g.w;
+    bool host = mem == NIDX_MEM_HOST;
+    float* dq; uint32_t* planes; RabitqQueryParams* params;
+    int r = rabitq_prepare_queries(s, w, queries, nq, ldq, host, stream, &dq, &planes, &params);
+    if (r) return r;
+    float *d_est = out_est, *d_err = out_err;
+    if (host) {
+        ENSURE(w.scores, (size_t)nq * s->n * 8);
+        d_est = w.scores.as<float>(); d_err = d_est + (size_t)nq * s->n;
+    }
+    if (s->n) {
+        rabitq_estimate_kernel<<<dim3((unsigned)((s->n + 255) / 256), nq), 256, 0, stream>>>(s->d_quant, s->quant_stride, (uint32_t)s->n, s->d, planes, params, d_est, d_err);
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+    if (host) {
+        CU(cudaMemcpyAsync(out_est, d_est, (size_t)nq * s->n * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_err, d_err, (size_t)nq * s->n * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
     return 0;
 }
 
@@ -546,7 +639,36 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
         if (host || !out_counts) d_cnt = w.out_counts.as<int>();
     }
 
-    if (s->n == 0) {
+    if (method == NIDX_METHOD_BRUTE_RABITQ && s->n != 0) {
+        // segment.rs:581-608 with SearchVector::RabitQ: estimate every vector from its 1-bit code, keep upper_bound >= min_score,
+        // rerank_top with the raw vectors (sequential semantics preserved, see rabitq_rerank_kernel)
+        int rr = rabitq_check(s);
+        if (rr) return rr;
+        if (!s->d_quant) return fail(NIDX_ESTATE, "segment has no RaBitQ codes (call nidx_vec_rabitq_encode)");
+        if (s->d_par_first) return fail(NIDX_EINVAL, "RaBitQ scan of multi-vector paragraphs is not implemented");
+        if (k > 1024) return fail(NIDX_EINVAL, "k above 1024 not supported");
+        uint32_t* planes; RabitqQueryParams* params; float* dq2;
+        rr = rabitq_prepare_queries(s, w, queries, nq, ldq, host, stream, &dq2, &planes, &params);
+        if (rr) return rr;
+        int qgroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)nq, ((size_t)4 << 30) / ((size_t)s->n * 8)));
+        ENSURE(w.scores, (size_t)qgroup * s->n * 8);
+        size_t smem_rr = rr_smem_bytes(s->ld, k);
+        CU(cudaFuncSetAttribute(rabitq_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rr));
+        for (int q0 = 0; q0 < nq; q0 += qgroup) {
+            int nqg = std::min(qgroup, nq - q0);
+            float* d_est = w.scores.as<float>();
+            float* d_err = d_est + (size_t)nqg * s->n;
+            if (q0 == 0) CU(cudaEventRecord(s->ev_k0, stream));
+            rabitq_estimate_kernel<<<dim3((unsigned)((s->n + 255) / 256), nqg), 256, 0, stream>>>(s->d_quant, s->quant_stride, (uint32_t)s->n, s->d,
+                                                                                                   planes + (size_t)q0 * 4 * (s->d / 32), params + q0, d_est, d_err);
+            if (q0 == 0) CU(cudaEventRecord(s->ev_k1, stream));
+            LAUNCHED();
+            rabitq_rerank_kernel<<<nqg, RR_THREADS, smem_rr, stream>>>(V, dq2 + (size_t)q0 * s->ld, d_est, d_err, bits, p->min_score, k, d_ids + (size_t)q0 * k,
+                                                                       d_sc + (size_t)q0 * k, d_cnt + q0, nullptr);
+            LAUNCHED();
+        }
+        CU(cudaGetLastError());
+    } else if (s->n == 0) {
         CU(cudaMemsetAsync(d_ids, 0xFF, (size_t)nq * k * 4, stream));
         CU(cudaMemsetAsync(d_sc, 0, (size_t)nq * k * 4, stream));
         CU(cudaMemsetAsync(d_cnt, 0, (size_t)nq * 4, stream));

@@ -142,6 +142,23 @@ class VectorSegment:
                                 None))
         return ids, scores, counts
 
+    # ---- RaBitQ (vector_types/rabitq.rs) ----------------------------------------------------------------
+    def rabitq_encode(self):
+        check(_lib.load().nidx_vec_rabitq_encode(self._h, None))
+
+    def rabitq_codes(self) -> np.ndarray:
+        out = np.empty((len(self), self.cfg.dimension // 8 + 8), dtype=np.uint8)
+        check(_lib.load().nidx_vec_rabitq_codes(self._h, ptr(out)))
+        return out
+
+    def rabitq_estimate(self, queries):
+        queries = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        nq = queries.shape[0]
+        est = np.empty((nq, len(self)), dtype=np.float32)
+        err = np.empty((nq, len(self)), dtype=np.float32)
+        check(_lib.load().nidx_vec_rabitq_estimate(self._h, ptr(queries), C.c_int32(nq), C.c_int32(queries.shape[1]), _lib.NIDX_MEM_HOST, ptr(est), ptr(err), None))
+        return est, err
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         check(_lib.load().nidx_vec_last_kernel_ms(self._h, C.byref(ms)))

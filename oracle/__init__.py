@@ -300,3 +300,53 @@ def bm25_search(P: Postings, queries, k, mode=BM25_OR, use_tf=True, alive_bits=N
                                    C.c_int(nq), C.c_int(mode), C.c_int(int(use_tf)), C.c_int(k), _p(docs), _p(sc), _p(cnt), _p(total),
                                    C.c_int(nthreads))
     return docs, sc, cnt, total
+
+
+# ---- RaBitQ (rabitq.rs) ---------------------------------------------------------------------------------
+def rabitq_encoded_len(d: int) -> int:
+    lib().oracle_rabitq_encoded_len.restype = C.c_uint64
+    return int(lib().oracle_rabitq_encoded_len(C.c_int(d)))
+
+
+def rabitq_encode(vecs, nthreads=1) -> np.ndarray:
+    """[n][d] f32 -> [n][d/8 + 8] bytes: [f32 dot_quant_original][u32 sum_bits][sign bits] (rabitq.rs:75-106)."""
+    vecs = _f32(np.atleast_2d(vecs))
+    n, d = vecs.shape
+    out = np.empty((n, rabitq_encoded_len(d)), dtype=np.uint8)
+    lib().oracle_rabitq_encode(_p(vecs), C.c_uint32(n), C.c_int(d), C.c_int(d), _p(out), C.c_int(nthreads))
+    return out
+
+
+def rabitq_estimate(enc, d, queries, nthreads=1):
+    """-> (estimate [nq][n], error [nq][n]) (rabitq.rs:202-218)."""
+    enc = np.ascontiguousarray(enc, dtype=np.uint8)
+    queries = _f32(np.atleast_2d(queries))
+    n, nq = enc.shape[0], queries.shape[0]
+    est = np.empty((nq, n), dtype=np.float32)
+    err = np.empty((nq, n), dtype=np.float32)
+    lib().oracle_rabitq_estimate(_p(enc), C.c_uint32(n), C.c_int(d), _p(queries), C.c_int(nq), C.c_int(queries.shape[1]), _p(est), _p(err), C.c_int(nthreads))
+    return est, err
+
+
+def rabitq_query(q):
+    q = _f32(q)
+    d = q.size
+    planes = np.empty((4, d // 64), dtype=np.uint64)
+    low, delta, sq = C.c_float(), C.c_float(), C.c_uint32()
+    lib().oracle_rabitq_query(_p(q), C.c_int(d), _p(planes), C.byref(low), C.byref(delta), C.byref(sq))
+    return planes, low.value, delta.value, sq.value
+
+
+def rabitq_brute_force(vecs, enc, queries, k, min_score=0.0, nthreads=1):
+    """segment.rs:581-608 with a RaBitQ query: estimates -> upper bound filter -> rerank_top (exact dot)."""
+    vecs, queries = _f32(vecs), _f32(np.atleast_2d(queries))
+    enc = np.ascontiguousarray(enc, dtype=np.uint8)
+    n, d = vecs.shape
+    nq = queries.shape[0]
+    ids = np.empty((nq, k), dtype=np.uint32)
+    sc = np.empty((nq, k), dtype=np.float32)
+    cnt = np.empty(nq, dtype=np.int32)
+    evals = np.empty(nq, dtype=np.uint64)
+    lib().oracle_rabitq_brute_force(_p(vecs), C.c_uint32(n), C.c_int(d), C.c_int(d), _p(enc), _p(queries), C.c_int(nq), C.c_int(d), C.c_int(k),
+                                    C.c_float(min_score), _p(ids), _p(sc), _p(cnt), _p(evals), C.c_int(nthreads))
+    return ids, sc, cnt, evals

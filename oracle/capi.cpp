@@ -11,6 +11,7 @@
 #include "bm25.hpp"
 #include "distance.hpp"
 #include "hnsw.hpp"
+#include "rabitq.hpp"
 #include "segment.hpp"
 
 using namespace nidx_oracle;
@@ -192,6 +193,54 @@ int oracle_fssc_result(void* h, uint32_t* segments, uint32_t* addrs, float* scor
     auto r = ((Fssc*)h)->sorted();
     for (size_t i = 0; i < r.size(); ++i) { segments[i] = r[i].segment; addrs[i] = r[i].addr; scores[i] = r[i].score; }
     return (int)r.size();
+}
+
+// ---- RaBitQ (rabitq.rs) ---------------------------------------------------------------------------
+uint64_t oracle_rabitq_encoded_len(int d) { return rabitq_encoded_len(d); }
+void oracle_rabitq_encode(const float* vecs, uint32_t n, int d, int ld, unsigned char* out, int nthreads) {
+    size_t len = rabitq_encoded_len(d);
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int64_t i = 0; i < (int64_t)n; ++i) rabitq_encode(vecs + (size_t)i * ld, d, out + (size_t)i * len);
+}
+// estimate / error of every encoded vector for nq queries: out_* are [nq][n]
+void oracle_rabitq_estimate(const unsigned char* enc, uint32_t n, int d, const float* queries, int nq, int qld, float* out_est, float* out_err,
+                            int nthreads) {
+    size_t len = rabitq_encoded_len(d);
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int qi = 0; qi < nq; ++qi) {
+        RabitqQuery rq = RabitqQuery::from_vector(queries + (size_t)qi * qld, d);
+        for (uint32_t v = 0; v < n; ++v) rq.similarity(enc + (size_t)v * len, out_est + (size_t)qi * n + v, out_err + (size_t)qi * n + v);
+    }
+}
+// query side of the quantisation, for checking the kernel's preparation: planes [4][d/64] u64, scalars low, delta, sum_quantized
+void oracle_rabitq_query(const float* q, int d, uint64_t* planes, float* low, float* delta, uint32_t* sum_quantized) {
+    RabitqQuery rq = RabitqQuery::from_vector(q, d);
+    for (int p = 0; p < 4; ++p) std::memcpy(planes + (size_t)p * (d / 64), rq.plane[p].data(), (size_t)d / 8);
+    *low = rq.low; *delta = rq.delta; *sum_quantized = rq.sum_quantized;
+}
+// brute force with RaBitQ (segment.rs:581-608): estimate every vector, keep upper_bound >= min_score, rerank_top with exact dot
+void oracle_rabitq_brute_force(const float* vecs, uint32_t n, int d, int ld, const unsigned char* enc, const float* queries, int nq, int qld, int k,
+                               float min_score, uint32_t* out_ids, float* out_scores, int* out_count, uint64_t* out_exact_evals, int nthreads) {
+    size_t len = rabitq_encoded_len(d);
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+    for (int qi = 0; qi < nq; ++qi) {
+        const float* q = queries + (size_t)qi * qld;
+        RabitqQuery rq = RabitqQuery::from_vector(q, d);
+        std::vector<std::pair<uint32_t, float>> cand;
+        for (uint32_t v = 0; v < n; ++v) {
+            float est, err;
+            rq.similarity(enc + (size_t)v * len, &est, &err);
+            if (est + err >= min_score) cand.push_back({v, est + err});   // EstimatedScore::new_with_error: upper_bound = score + error
+        }
+        uint64_t evals = 0;
+        auto r = rerank_top(cand, (size_t)k, min_score, [&](uint32_t v) { evals++; return dot_ordered(vecs + (size_t)v * ld, q, d); });
+        if (out_exact_evals) out_exact_evals[qi] = evals;
+        out_count[qi] = (int)r.size();
+        for (int j = 0; j < k; ++j) {
+            out_ids[(size_t)qi * k + j] = j < (int)r.size() ? r[j].id : NIL;
+            out_scores[(size_t)qi * k + j] = j < (int)r.size() ? r[j].score : 0.0f;
+        }
+    }
 }
 
 // ---- BM25 ---------------------------------------------------------------------------------------

@@ -216,3 +216,47 @@ def test_bm25_min_score_counts_like_reference_tests():
     assert list(docs[0, : cnt[0]]) == [1]
     docs, sc, cnt, total = O.bm25_search(P, [[0, 7]], 10, mode=O.BM25_OR, use_tf=False)
     assert total[0] == 3
+
+
+# ---- nidx_vector/src/vector_types/rabitq.rs:284-306 test_rabitq_estimate + layout 70-106 ---------------------------
+def test_rabitq_estimate_error_bound_and_layout():
+    rng = np.random.default_rng(123)
+    D = 2048
+
+    def random_vector():
+        v = rng.uniform(-1, 1, D).astype(np.float32)
+        return (v / np.sqrt((v * v).sum())).astype(np.float32)
+
+    v1 = random_vector()
+    fuzz = random_vector()
+    v2 = v1 + fuzz * np.float32(0.1)
+    v2 = (v2 / np.sqrt((v2 * v2).sum())).astype(np.float32)
+    v3 = random_vector()
+    enc = O.rabitq_encode(v1[None, :])
+    assert enc.shape == (1, D // 8 + 8)                                   # encoded_len
+    dqo, sum_bits = struct.unpack_from("<fI", enc[0].tobytes(), 0)
+    assert sum_bits == int((v1 > 0).sum())
+    bits = np.unpackbits(enc[0, 8:], bitorder="little")
+    assert (bits.astype(bool) == (v1 > 0)).all()                          # bit i of word i/64 = sign of element i
+    assert abs(dqo - float(np.abs(v1).sum() / np.sqrt(D))) < 1e-4         # <v, sign(v)/sqrt(D)>
+    for other in (v2, v3):                                                # high and low similarity
+        est, err = O.rabitq_estimate(enc, D, other[None, :])
+        actual = float(np.dot(v1.astype(np.float64), other.astype(np.float64)))
+        assert abs(actual - float(est[0, 0])) < float(err[0, 0]) and float(err[0, 0]) < 0.05
+    planes, low, delta, sq = O.rabitq_query(v2)
+    wq = np.floor((v2 - np.float32(low)) / np.float32(delta)).astype(np.int64)
+    assert wq.min() == 0 and wq.max() == 15 and sq == int(wq.sum())
+    for p in range(4):
+        assert (np.unpackbits(planes[p].view(np.uint8), bitorder="little").astype(np.int64) == ((wq >> p) & 1)).all()
+
+
+def test_rabitq_brute_force_finds_the_exact_top_k():
+    from conftest import make_queries, make_vectors
+    v = make_vectors(4000, 256, seed=31)
+    q = make_queries(v, 16)
+    enc = O.rabitq_encode(v, nthreads=4)
+    ids, sc, cnt, evals = O.rabitq_brute_force(v, enc, q, 10, min_score=0.0, nthreads=4)
+    bi, bs, bc = O.brute_force(v, q, 10, sim=O.SIM_DOT, min_score=0.0, nthreads=4)
+    assert (cnt == bc).all()
+    assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ids, bi)]) >= 0.99     # the bound holds with ~97 % confidence per pair
+    assert (evals < 4000).all() and evals.mean() < 1500                              # most raw vectors are never touched
