@@ -39,18 +39,6 @@ __global__ void row_norms_kernel(const float* __restrict__ rows, int ld, uint64_
     }
 }
 
-// utils.rs:20-23 normalize_vector: magnitude folded sequentially in f32; x / magnitude.  One thread
-// per row (queries only; tiny).
-__global__ void normalize_rows_kernel(float* rows, int d, int ld, int n) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    float* x = rows + (size_t)r * ld;
-    float acc = 0.0f;
-    for (int i = 0; i < d; ++i) acc = __fadd_rn(acc, __fmul_rn(x[i], x[i]));
-    float mag = __fsqrt_rn(acc);
-    for (int i = 0; i < d; ++i) x[i] = __fdiv_rn(x[i], mag);
-}
-
 constexpr int SCAN_WARPS = 8;
 constexpr int SCAN_QT = 8;      // queries per tile (shared memory)
 constexpr int SCAN_VPW = 32;    // vectors per warp (one score per lane => coalesced stores)

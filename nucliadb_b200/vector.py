@@ -478,3 +478,27 @@ class VectorIndexer:
     @staticmethod
     def index_elems(elems: Sequence[Elem], config: VectorConfig, tags=frozenset(), **kw) -> OpenSegment:
         return OpenSegment.create(elems, config, tags, **kw)
+
+    @staticmethod
+    def merge(config: VectorConfig, segments: Sequence[tuple], deletions: Sequence[tuple] = (), **kw) -> OpenSegment:
+        """lib.rs:97-117 + segment.rs:92-135: open the segments applying deletions by sequence (a deletion applies to a
+        segment iff del.seq > segment.seq), copy the alive paragraphs -- largest segment first -- into one data store and
+        build its HNSW on the GPU.  The reference reuses the largest segment's graph when it has no deletions
+        (segment.rs:143-167); here the merged graph is always rebuilt (SURVEY 8f rank 3 is the reuse)."""
+        opened = []
+        for seg, seq in segments:
+            dels = [k for k, dseq in deletions if dseq > seq]
+            if dels:
+                seg.apply_deletions(dels)
+            opened.append(seg)
+        opened.sort(key=lambda s: -int(s.alive.sum()))
+        elems, tags = [], set()
+        for seg in opened:
+            tags |= set(seg.tags)
+            for p in np.nonzero(seg.alive)[0]:
+                a, b = int(seg.first_vec[p]), int(seg.first_vec[p + 1])
+                elems.append(Elem(seg.keys[p], [seg.host_vectors[i] for i in range(a, b)], seg.labels[p], seg.metadata[p]))
+        merged_cfg = VectorConfig(**{**config.__dict__, "normalize_vectors": False})   # vectors were normalised when first indexed
+        out = OpenSegment.create(elems, merged_cfg, frozenset(tags), **kw)
+        out.config = config
+        return out

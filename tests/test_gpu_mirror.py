@@ -204,3 +204,19 @@ def test_paragraph_search_after():  # nidx_paragraph/src/reader.rs:350-392 is_af
     assert none.results == []
     keep = p.search(T.DocumentSearchRequest(body="prince", result_per_page=20, search_after=T.SearchAfter(full.results[3].score.bm25, "keep")))
     assert [r.uuid for r in keep.results] == [r.uuid for r in full.results if r.score.bm25 <= full.results[3].score.bm25]
+
+
+def test_merge_segments_with_deletions():  # nidx_vector/src/segment/tests.rs merge flows + lib.rs:166-200
+    cfg = V.VectorConfig(dimension=DIM, similarity=V.Similarity.Dot)
+    other = "00000000000000000000000000000002"
+    seg1 = V.VectorIndexer.index_elems([V.Elem(f"{RID}/a/title/0-{i}", [sentence(i)], labels=["/l/one"]) for i in range(20)], cfg)
+    seg2 = V.VectorIndexer.index_elems([V.Elem(f"{other}/a/title/0-{i}", [sentence(i + 20)], labels=["/l/two"]) for i in range(30)], cfg)
+    merged = V.VectorIndexer.merge(cfg, [(seg1, 1), (seg2, 3)], deletions=[(RID, 2), (other, 2)])
+    assert merged.records == 30 and all(k.startswith(other) for k in merged.keys)       # seq-2 deletion only hits seg1 (seq 1)
+    searcher = V.VectorSearcher.open(cfg, [(merged, 4)])
+    r = searcher.search(V.VectorSearchRequest(vector=sentence(25), result_per_page=3, min_score=-1.0))
+    assert r.documents[0].doc_id == f"{other}/a/title/0-5" and r.documents[0].score > 0.9999
+    r = searcher.search(V.VectorSearchRequest(vector=sentence(25), result_per_page=3, min_score=-1.0, filtering_formula=V.Literal("/l/one")))
+    assert r.documents == []
+    both = V.VectorIndexer.merge(cfg, [(V.VectorIndexer.index_elems([V.Elem(f"{RID}/a/title/0-{i}", [sentence(i)]) for i in range(5)], cfg), 1), (merged, 4)])
+    assert both.records == 35 and both.keys[0].startswith(other)                         # largest segment first (segment.rs:103-105)
