@@ -129,6 +129,45 @@ def bench_build(args):
     return lines
 
 
+def bench_merge(args):
+    """merge_indexes (segment.rs:143-167): a segment of --build-vectors vectors without deletions plus 10% new vectors.  The
+    graph of the large segment is reused and only the new vectors are inserted; timed beside the full rebuild."""
+    import torch
+
+    from bench import gen_queries, gen_vectors, recall_at_k
+    from nucliadb_b200 import _lib
+    from nucliadb_b200.segment import VectorSegment
+
+    dev = torch.device("cuda", 0)
+    n0, d = args.build_vectors, 768
+    n = n0 + n0 // 10
+    vecs = gen_vectors(n, d, dev, seed=1234567890, latent=16, noise=0.15)
+    q = gen_queries(vecs, 1024, seed=123)
+    kw = dict(similarity=_lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=200)
+    first = VectorSegment.create(vecs[:n0].contiguous(), d, **kw)
+    first.build_hnsw(seed=2, max_batch=8192)
+    g = first.get_graph()
+    first.close()
+    rows = max(int(g["upper_rows"]), 1)
+    out = {}
+    for name in ("reuse", "rebuild"):
+        seg = VectorSegment.create(vecs, d, **kw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if name == "reuse":
+            seg.extend_hnsw(n0, g["level"], g["adj0"], g["adjU"][:rows], g["w0"], g["wU"][:rows], g["entry_node"], g["entry_layer"], seed=2, max_batch=8192)
+        else:
+            seg.build_hnsw(seed=2, max_batch=8192)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        gt = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)[0].cpu().numpy()
+        out[name] = {"seconds": dt, "recall_at_10_ef128": recall_at_k(seg.search(q, 10, ef=128, method=_lib.NIDX_METHOD_HNSW)[0].cpu().numpy(), gt)}
+        seg.close()
+    return [{"metric": "merge inserted vectors/s", "value": (n - n0) / out["reuse"]["seconds"], "unit": "vectors/s", "n_gpus": 1, "higher_is_better": True,
+             "dtype": "f32", "data": "synthetic", "config": {"workload": f"merge {n0}x{d} (graph reused) + {n - n0} new, M=16 M0=32 efC=200", "max_batch": 8192},
+             "reuse": out["reuse"], "rebuild": out["rebuild"], "note": "reuse time includes the host->device copy of the existing graph"}]
+
+
 def make_corpus(n_docs, n_terms, dev, seed=7, mean_len=64, zipf_s=1.07):
     """5M docs, vocabulary 1M Zipf(1.07), doc length lognormal (mean 64) — BASELINE.md row 4.  Built on the GPU with torch
     (sorting 3e8 tokens on the host takes minutes); returned as host CSR arrays."""
@@ -227,7 +266,7 @@ def bench_bm25(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["scan", "bm25", "build", "all"])
+    ap.add_argument("which", choices=["scan", "bm25", "build", "merge", "all"])
     ap.add_argument("--build-vectors", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -240,6 +279,8 @@ def main():
         lines += bench_bm25(args)
     if args.which in ("build", "all"):
         lines += bench_build(args)
+    if args.which == "merge":
+        lines += bench_merge(args)
     for line in lines:
         print(json.dumps(line))
 

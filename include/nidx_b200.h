@@ -96,6 +96,14 @@ const float* nidx_vec_device_vectors(const nidx_vec_segment* seg, int32_t* ld_ou
  * the frozen graph and are linked in ascending id.  seed: level RNG seed (reference uses 2). */
 int nidx_vec_build_hnsw(nidx_vec_segment* seg, uint64_t seed, int32_t max_batch, void* stream);
 
+/* merge_indexes' fast path (segment.rs:143-167): the first n_existing vectors of this segment already have a graph
+ * (the largest input segment of a merge, without deletions) given in the flat layout below for n_existing nodes; only the
+ * remaining vectors are inserted.  Levels of the new nodes come from a fresh RNG (HnswBuilder::new + initialize_graph with
+ * skip_nodes = n_existing, build.rs:36-55); the entry point moves only if a higher layer appears (ram_hnsw.rs:99-107). */
+int nidx_vec_extend_hnsw(nidx_vec_segment* seg, uint64_t n_existing, const uint8_t* level_existing, const uint32_t* adj0, const float* w0,
+                         const uint32_t* adjU, const float* wU, uint32_t entry_node, uint32_t entry_layer, uint64_t seed, int32_t max_batch,
+                         void* stream);
+
 /* Flat graph import / export (the layout in DESIGN.md; the oracle uses the same one).
  * level[n] u8; adj0[n][s0] u32, adjU[rows][su] u32, NIDX_NIL padded; w0/wU edge similarities
  * (may be NULL on import: search does not need them, merge/build does). Host pointers. */

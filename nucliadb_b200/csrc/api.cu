@@ -801,29 +801,14 @@ static void host_assign_levels(uint64_t n, int M, uint64_t seed, uint8_t* level)
     }
 }
 
-int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, void* stream_) {
-    if (!s) return fail(NIDX_EINVAL, "null segment");
-    CU(cudaSetDevice(s->cfg.device));
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    uint64_t n = s->n;
-    if (max_batch <= 0) max_batch = 4096;
-    std::vector<uint8_t> level(n ? n : 1);
-    host_assign_levels(n, s->cfg.m, seed, level.data());
-    int r = alloc_graph(s, level.data());
-    if (r) return r;
-    s->has_graph = true;
-    if (n == 0) return 0;
+}  // extern "C"
 
-    // insertion order: entry point first, then ascending id; batch b = min(max_batch, max(1, done/16))
-    std::vector<uint32_t> order(n);
-    order[0] = s->entry_node;
-    for (uint64_t i = 0, j = 1; i < n; ++i) if (i != s->entry_node) order[j++] = (uint32_t)i;
-    std::vector<uint32_t> ends;
-    for (uint64_t done = 0; done < n;) {
-        uint64_t b = std::min<uint64_t>({(uint64_t)max_batch, std::max<uint64_t>(1, done / 16), n - done});
-        done += b;
-        ends.push_back((uint32_t)done);
-    }
+// Batch-synchronous insertion of order[0 .. n) into the segment's graph (which may already hold other nodes):
+// the loop of build.rs:123-166 as search / select / sort / reverse-link kernels per batch (hnsw_build.cuh).
+static int run_insertions(nidx_vec_segment* s, const std::vector<uint8_t>& level, const std::vector<uint32_t>& order, const std::vector<uint32_t>& ends,
+                          cudaStream_t stream) {
+    uint64_t n = order.size();
+    int r = 0;
     // work items (node position, layer), insertion order, layer ascending
     std::vector<uint64_t> wstart(n + 1);
     uint64_t W = 0;
@@ -951,6 +936,80 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
         return 0;
     }();
     cleanup();
+    return r;
+}
+
+extern "C" {
+
+int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, void* stream_) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    uint64_t n = s->n;
+    if (max_batch <= 0) max_batch = 4096;
+    std::vector<uint8_t> level(n ? n : 1);
+    host_assign_levels(n, s->cfg.m, seed, level.data());
+    int r = alloc_graph(s, level.data());
+    if (r) return r;
+    s->has_graph = true;
+    if (n == 0) return 0;
+
+    // insertion order: entry point first, then ascending id; batch b = min(max_batch, max(1, done/16))
+    std::vector<uint32_t> order(n);
+    order[0] = s->entry_node;
+    for (uint64_t i = 0, j = 1; i < n; ++i) if (i != s->entry_node) order[j++] = (uint32_t)i;
+    std::vector<uint32_t> ends;
+    for (uint64_t done = 0; done < n;) {
+        uint64_t b = std::min<uint64_t>({(uint64_t)max_batch, std::max<uint64_t>(1, done / 16), n - done});
+        done += b;
+        ends.push_back((uint32_t)done);
+    }
+    r = run_insertions(s, level, order, ends, stream);
+    if (r) { free_graph(s); return r; }
+    return 0;
+}
+
+// merge_indexes' fast path (segment.rs:143-167): the first n_existing vectors of this (merged) segment are the largest
+// input segment, which had no deletions, so its graph is reused and only the remaining vectors are inserted.
+// HnswBuilder::new seeds a fresh level RNG and initialize_graph(skip_nodes = n_existing, total) draws the new nodes'
+// levels (build.rs:36-55); the entry point moves only if a higher layer appears (ram_hnsw.rs:99-107).
+int nidx_vec_extend_hnsw(nidx_vec_segment* s, uint64_t n_existing, const uint8_t* level_existing, const uint32_t* adj0, const float* w0,
+                         const uint32_t* adjU, const float* wU, uint32_t entry_node, uint32_t entry_layer, uint64_t seed, int32_t max_batch, void* stream_) {
+    if (!s || !level_existing || !adj0) return fail(NIDX_EINVAL, "null argument");
+    if (n_existing == 0 || n_existing > s->n) return fail(NIDX_EINVAL, "n_existing must be in 1..len");
+    if (entry_node >= n_existing || level_existing[entry_node] < entry_layer) return fail(NIDX_EINVAL, "bad entry point");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    uint64_t n = s->n;
+    if (max_batch <= 0) max_batch = 4096;
+    std::vector<uint8_t> level(n);
+    memcpy(level.data(), level_existing, n_existing);
+    for (uint64_t i = 0; i < n_existing; ++i)
+        if (level[i] >= HS_MAX_LAYERS) return fail(NIDX_EINVAL, "node %llu has level %d >= %d", (unsigned long long)i, level[i], HS_MAX_LAYERS);
+    host_assign_levels(n - n_existing, s->cfg.m, seed, level.data() + n_existing);
+    int r = alloc_graph(s, level.data());
+    if (r) return r;
+    uint32_t new_top = s->entry_layer, new_entry = s->entry_node;   // alloc_graph: lowest id of the global top layer
+    if (new_top <= entry_layer) { s->entry_layer = entry_layer; s->entry_node = entry_node; }
+    else { s->entry_layer = new_top; s->entry_node = new_entry; }
+    // the existing nodes' rows: layer 0 rows are a prefix, and so are their upper-pool rows (offsets depend on earlier nodes only)
+    uint64_t rows_existing = 0;
+    for (uint64_t i = 0; i < n_existing; ++i) rows_existing += level[i];
+    CU(cudaMemcpy(s->d_adj0, adj0, (size_t)n_existing * s->s0 * 4, cudaMemcpyHostToDevice));
+    if (w0) CU(cudaMemcpy(s->d_w0, w0, (size_t)n_existing * s->s0 * 4, cudaMemcpyHostToDevice));
+    if (rows_existing && adjU) CU(cudaMemcpy(s->d_adjU, adjU, (size_t)rows_existing * s->su * 4, cudaMemcpyHostToDevice));
+    if (rows_existing && wU) CU(cudaMemcpy(s->d_wU, wU, (size_t)rows_existing * s->su * 4, cudaMemcpyHostToDevice));
+    s->has_graph = true;
+    if (n == n_existing) return 0;
+    std::vector<uint32_t> order(n - n_existing);
+    for (uint64_t i = n_existing; i < n; ++i) order[i - n_existing] = (uint32_t)i;
+    std::vector<uint32_t> ends;
+    for (uint64_t done = n_existing; done < n;) {
+        uint64_t b = std::min<uint64_t>({(uint64_t)max_batch, std::max<uint64_t>(1, done / 16), n - done});
+        done += b;
+        ends.push_back((uint32_t)(done - n_existing));
+    }
+    r = run_insertions(s, level, order, ends, stream);
     if (r) { free_graph(s); return r; }
     return 0;
 }

@@ -80,6 +80,16 @@ class VectorSegment:
     def build_hnsw(self, seed=2, max_batch=4096):
         check(_lib.load().nidx_vec_build_hnsw(self._h, C.c_uint64(seed), C.c_int32(max_batch), None))
 
+    def extend_hnsw(self, n_existing, level, adj0, adjU, w0, wU, entry_node, entry_layer, seed=2, max_batch=4096):
+        """Reuse the graph of the first n_existing vectors and insert the rest (segment.rs:143-167)."""
+        level = np.ascontiguousarray(level, dtype=np.uint8)
+        adj0 = np.ascontiguousarray(adj0, dtype=np.uint32)
+        adjU = np.ascontiguousarray(adjU, dtype=np.uint32)
+        w0 = np.ascontiguousarray(w0, dtype=np.float32)
+        wU = np.ascontiguousarray(wU, dtype=np.float32)
+        check(_lib.load().nidx_vec_extend_hnsw(self._h, C.c_uint64(n_existing), ptr(level), ptr(adj0), ptr(w0), ptr(adjU), ptr(wU), C.c_uint32(entry_node),
+                                               C.c_uint32(entry_layer), C.c_uint64(seed), C.c_int32(max_batch), None))
+
     def graph_dims(self):
         s0, su, rows, en, el = C.c_int32(), C.c_int32(), C.c_uint64(), C.c_uint32(), C.c_uint32()
         check(_lib.load().nidx_vec_graph_dims(self._h, C.byref(s0), C.byref(su), C.byref(rows), C.byref(en), C.byref(el)))

@@ -481,24 +481,47 @@ class VectorIndexer:
 
     @staticmethod
     def merge(config: VectorConfig, segments: Sequence[tuple], deletions: Sequence[tuple] = (), **kw) -> OpenSegment:
-        """lib.rs:97-117 + segment.rs:92-135: open the segments applying deletions by sequence (a deletion applies to a
-        segment iff del.seq > segment.seq), copy the alive paragraphs -- largest segment first -- into one data store and
-        build its HNSW on the GPU.  The reference reuses the largest segment's graph when it has no deletions
-        (segment.rs:143-167); here the merged graph is always rebuilt (SURVEY 8f rank 3 is the reuse)."""
+        """lib.rs:97-117 + segment.rs:92-197: open the segments applying deletions by sequence (a deletion applies to a
+        segment iff del.seq > segment.seq), copy the alive paragraphs -- segment with most stored records first -- into one
+        data store.  If that first segment has no deletions its HNSW is reused (its vector addresses are a prefix of the
+        merged store's) and only the other segments' vectors are inserted (merge_indexes, segment.rs:143-167); otherwise the
+        graph is built from scratch.  Both on the GPU."""
+        from .segment import VectorSegment
+
         opened = []
         for seg, seq in segments:
             dels = [k for k, dseq in deletions if dseq > seq]
             if dels:
                 seg.apply_deletions(dels)
             opened.append(seg)
-        opened.sort(key=lambda s: -int(s.alive.sum()))
-        elems, tags = [], set()
+        opened.sort(key=lambda s: -int(s.records))
+        if any(s.tags != opened[0].tags for s in opened):
+            raise NidxError(-1, "InconsistentMergeSegmentTags")
+        elems = []
         for seg in opened:
-            tags |= set(seg.tags)
             for p in np.nonzero(seg.alive)[0]:
                 a, b = int(seg.first_vec[p]), int(seg.first_vec[p + 1])
                 elems.append(Elem(seg.keys[p], [seg.host_vectors[i] for i in range(a, b)], seg.labels[p], seg.metadata[p]))
         merged_cfg = VectorConfig(**{**config.__dict__, "normalize_vectors": False})   # vectors were normalised when first indexed
-        out = OpenSegment.create(elems, merged_cfg, frozenset(tags), **kw)
+        first = opened[0]
+        view = VectorSegment(first._h, None)        # borrowed handles: the OpenSegments own them
+        tgt = VectorSegment(None, None)
+        try:
+            reuse = bool(first.alive.all()) and len(first.host_vectors) > 0
+            if reuse:
+                try:
+                    g = view.get_graph()
+                except NidxError:                       # the first segment was created without a graph
+                    reuse = False
+            if reuse:
+                out = OpenSegment.create(elems, merged_cfg, frozenset(first.tags), build_graph=False)
+                tgt._h = out._h
+                rows = max(int(g["upper_rows"]), 1)
+                tgt.extend_hnsw(len(first.host_vectors), g["level"], g["adj0"], g["adjU"][:rows], g["w0"], g["wU"][:rows], g["entry_node"], g["entry_layer"],
+                                seed=kw.get("seed", 2), max_batch=kw.get("max_batch", 4096))
+            else:
+                out = OpenSegment.create(elems, merged_cfg, frozenset(first.tags), **kw)
+        finally:
+            view._h = tgt._h = None
         out.config = config
         return out

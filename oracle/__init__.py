@@ -171,6 +171,34 @@ def hnsw_build(vecs, sim=SIM_COSINE, M=30, M0=60, efC=100, seed=2, max_batch=1, 
     return g
 
 
+def hnsw_extend(vecs, g0: Graph, sim=SIM_COSINE, efC=100, seed=2, max_batch=1, nthreads=1):
+    """merge_indexes' fast path (segment.rs:143-167): keep g0 (the graph of the first g0.n vectors) and insert the remaining
+    vectors; new levels from a fresh RNG (build.rs:36-55), entry point moved only if a higher layer appears."""
+    vecs = _f32(vecs)
+    n, d = vecs.shape
+    n0 = g0.n
+    level = np.concatenate([g0.level, assign_levels(n - n0, g0.M, seed)]).astype(np.uint8)
+    g = Graph(n, g0.M, g0.M0, level)
+    if g.entry_layer <= g0.entry_layer:
+        g.entry_node, g.entry_layer = g0.entry_node, g0.entry_layer
+    g.adj0[:n0], g.w0[:n0] = g0.adj0, g0.w0
+    rows0 = int(g0.level.astype(np.int64).sum())
+    g.adjU[:rows0], g.wU[:rows0] = g0.adjU[:rows0], g0.wU[:rows0]
+    nrm = norms(vecs, nthreads) if sim == SIM_COSINE else None
+    order = np.arange(n0, n, dtype=np.uint32)
+    ends, done = [], n0
+    while done < n:
+        b = min(max_batch, max(1, done // 16), n - done)
+        done += b
+        ends.append(done - n0)
+    ends = np.asarray(ends, dtype=np.uint32)
+    counters = np.zeros(3, dtype=np.uint64)
+    lib().oracle_hnsw_build(_p(vecs), _p(nrm), C.c_uint32(n), C.c_int(d), C.c_int(d), C.c_int(sim), C.c_int(g.M), C.c_int(g.M0), C.c_int(efC), _p(g.level),
+                            C.c_uint32(g.entry_node), C.c_uint32(g.entry_layer), _p(g.adj0), _p(g.w0), _p(g.upper_off), _p(g.adjU), _p(g.wU), _p(order), _p(ends),
+                            C.c_uint32(len(ends)), C.c_int(nthreads), _p(counters))
+    return g
+
+
 def hnsw_search(vecs, g: Graph, queries, k, ef, sim=SIM_COSINE, min_score=-1.0, with_duplicates=True, multi_vector=False, filter_bits=None,
                 paragraph_of=None, nthreads=1, native=False, norms_=None):
     """search.rs:306-383 for a batch -> (ids, scores, count, counters[n_dist, n_expand, n_edges_read])."""
