@@ -339,6 +339,12 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = float(np.mean(alg_bytes)) / (float(np.mean(kernel_ms)) * 1e-3) / 1e9
+    workload = f"HNSW search {n}x{d} cosine, ef={ef} k={k}, batch={nq}"
+    traffic = None            # DRAM bytes per launch from the committed ncu capture of this exact workload, if there is one
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
 
     # ---- e2e: the same metric through the host-buffer C ABI call (H2D + D2H inside the timed region) --
     hq = [torch.empty((nq, d), dtype=torch.float32).pin_memory() for _ in range(n_batches)]
@@ -374,6 +380,48 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_qps = world * nq * args.steps / e2e_dt
+    e2e_mode = {"calls_in_flight": 1, "one_call_at_a_time_qps": e2e_qps}
+    if not multi:
+        # The reference serves every request on its own blocking thread against a shared searcher (shard_search.rs:139-155); the
+        # same here: two host threads, each with its own stream, call the re-entrant entry point on alternate batches so that one
+        # call's copies overlap the other's kernel.  Every step still carries its own H2D and D2H inside the timed region.
+        import threading
+
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        errors = []
+
+        def worker(j):
+            try:
+                for i in range(args.warmup + j, n_batches, 2):
+                    seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, stream=streams[j].cuda_stream)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        def warm(j):
+            for i in range(j, max(args.warmup, 2), 2):
+                seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, stream=streams[j].cuda_stream)
+
+        threads = [threading.Thread(target=warm, args=(j,)) for j in range(2)]   # second workspace allocated outside the timed region
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        torch.cuda.synchronize()
+        with clocks:
+            threads = [threading.Thread(target=worker, args=(j,)) for j in range(2)]
+            t0 = time.perf_counter()
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            torch.cuda.synchronize()
+            dt2 = time.perf_counter() - t0
+        if errors:
+            raise errors[0]
+        qps2 = nq * args.steps / dt2
+        e2e_mode["two_calls_in_flight_qps"] = qps2
+        if qps2 > e2e_qps:
+            e2e_qps, e2e_mode["calls_in_flight"] = qps2, 2
 
     # ---- CPU baseline (rank 0, N=1): the oracle on the host cores, bounded sample ---------------------
     cpu = None
@@ -400,7 +448,7 @@ def main():
         line = {
             "metric": "k-NN QPS @ recall@10", "value": qps_units, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"HNSW search {n}x{d} cosine, ef={ef} k={k}, batch={nq}", "segments": world, "vectors_per_segment": n,
+            "config": {"workload": workload, "segments": world, "vectors_per_segment": n,
                        "M": m, "M0": m0, "efC": args.efc, "l2": "inputs larger than L2 (30.7 GB of vectors per GPU, fresh queries every step)",
                        "unit_note": "one unit = one query searched on one segment; merged_qps = user-visible queries/s over all segments",
                        "data_gen": f"latent={args.latent} noise={args.noise} normalised; queries = data point + 0.05 * unit noise"},
@@ -409,11 +457,11 @@ def main():
             "ef30": ef30,
             "build": {"seconds": t_build, "vectors_per_s": n / t_build, "similarities": build_counters["similarities"], "max_batch": args.max_batch,
                       "data_seconds": t_data},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "hnsw_search_kernel", "kernel_ms": float(np.mean(kernel_ms)), "alg_bytes_per_launch": float(np.mean(alg_bytes)),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "profiles/ncu_traffic.json" if traffic else None, "kernel": "hnsw_search_kernel", "kernel_ms": float(np.mean(kernel_ms)), "alg_bytes_per_launch": float(np.mean(alg_bytes)),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4, **e2e_mode},
             "gpu_launches": int(launches),
             "visited_overflows": int(overflow),
             "clocks": clocks.summary(),

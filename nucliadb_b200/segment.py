@@ -120,9 +120,10 @@ class VectorSegment:
 
     # ---- search ----------------------------------------------------------------------------------------
     def search(self, queries, k: int, ef: int = 0, min_score: float = -1.0, with_duplicates=True, method=_lib.NIDX_METHOD_AUTO,
-               filter_bits=None, filter_matching: int = 0, out=None):
+               filter_bits=None, filter_matching: int = 0, out=None, stream: Optional[int] = None):
         """Batch search.  numpy in -> numpy out (host path, synchronous); torch CUDA tensors in -> torch
-        CUDA tensors out (device path, asynchronous on the current stream).  Returns (ids, scores, counts)."""
+        CUDA tensors out (device path, asynchronous on the current stream).  `stream` (a cudaStream_t as int) lets concurrent
+        host-path callers overlap their copies with each other's kernels.  Returns (ids, scores, counts)."""
         L = _lib.load()
         p = VecSearchParams(k, ef, min_score, int(with_duplicates), method, None, filter_matching)
         if _is_torch(queries):
@@ -149,7 +150,7 @@ class VectorSegment:
             keep = np.ascontiguousarray(filter_bits, dtype=np.uint64)
             p.filter_bits = keep.ctypes.data
         check(L.nidx_vec_search(self._h, ptr(queries), C.c_int32(nq), C.c_int32(ldq), _lib.NIDX_MEM_HOST, C.byref(p), ptr(ids), ptr(scores), ptr(counts),
-                                None))
+                                C.c_void_p(stream) if stream else None))
         return ids, scores, counts
 
     # ---- RaBitQ (vector_types/rabitq.rs) ----------------------------------------------------------------

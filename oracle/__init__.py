@@ -121,6 +121,34 @@ def brute_force(vecs, queries, k, sim=SIM_COSINE, min_score=-1.0, alive_bits=Non
     return ids, sc, cnt
 
 
+def maxsim_similarity(query_vectors, doc_vectors, sim=SIM_COSINE) -> float:
+    """multivector.rs:34-46: sum over query vectors of max(0, best similarity to a vector of the document), f32 fold."""
+    total = np.float32(0.0)
+    for vq in query_vectors:
+        best = np.float32(0.0)
+        for vd in doc_vectors:
+            s = np.float32(cosine(vd, vq) if sim == SIM_COSINE else dot(vd, vq))
+            if s > best:
+                best = s
+        total = np.float32(total + best)
+    return float(total)
+
+
+def multi_vector_search(paragraphs, query_vectors, k, min_score, sim=SIM_COSINE):
+    """searcher.rs:345-394 on one exhaustive segment: every query vector retrieves (exact scan, duplicates allowed, no
+    min_score, at least 10 results) the paragraphs of its best vectors; the union is re-scored with MaxSim, filtered with a
+    strict `> min_score`, sorted and truncated.  paragraphs: list of [n_i, d] arrays.  -> [(paragraph index, score)]."""
+    first = np.cumsum([0] + [len(p) for p in paragraphs]).astype(np.uint32)
+    vecs = _f32(np.concatenate(paragraphs))
+    ids, _, counts = brute_force(vecs, _f32(query_vectors), max(k, 10), sim=sim, min_score=float(np.finfo(np.float32).min), first_vec=first[:-1],
+                                 num_vec=np.diff(first).astype(np.uint32))
+    cand = sorted({int(np.searchsorted(first, a, side="right") - 1) for qi in range(len(query_vectors)) for a in ids[qi, : counts[qi]]})
+    scored = [(p, maxsim_similarity(query_vectors, paragraphs[p], sim)) for p in cand]
+    scored = [(p, s) for p, s in scored if s > min_score]
+    scored.sort(key=lambda t: -t[1])
+    return scored[:k]
+
+
 class Graph:
     """Flat HNSW graph (the layout shared with the CUDA library)."""
 

@@ -162,6 +162,17 @@ def test_fssc_dedup_and_replacement():
     assert list(addr) == [1, 2] and list(sc) == [np.float32(0.7), np.float32(0.6)]
 
 
+# ---- nidx_vector/tests/test_maxsim.rs:22-150 ------------------------------------------------------------------------
+def test_maxsim_exact_scores():
+    e = np.eye(5, dtype=np.float32)
+    query = [e[0], e[3]]
+    docs = [np.stack([e[1], e[2], e[4]]), np.stack([e[0], e[1], e[2]]), np.stack([e[0], e[2], e[3]])]      # d0 (0), d1 (1), d2 (2)
+    assert O.multi_vector_search(docs, query, 1, -10.0) == [(2, 2.0)]
+    assert O.multi_vector_search(docs, query, 10, 1.5) == [(2, 2.0)]          # min_score applies to the MaxSim score only
+    assert O.multi_vector_search(docs, query, 2, -10.0) == [(2, 2.0), (1, 1.0)]
+    assert O.maxsim_similarity(query, docs[0]) == 0.0                          # negative / zero similarities never add
+
+
 # ---- nidx_vector/src/hnsw/disk/v2.rs:16-49 worked example + 349-398 hnsw_test ----------------------------------
 def test_disk_v2_worked_example_bytes():
     layers = [{0: [(1, 0.1), (17, 0.2), (5433, 0.3), (45, 0.4), (667, 0.5)]}, {0: [(45, 1.0), (666, 2.0), (22, 3.0)]}, {}]
