@@ -997,8 +997,39 @@ int nidx_vec_extend_hnsw(nidx_vec_segment* s, uint64_t n_existing, const uint8_t
     for (uint64_t i = 0; i < n_existing; ++i) rows_existing += level[i];
     CU(cudaMemcpy(s->d_adj0, adj0, (size_t)n_existing * s->s0 * 4, cudaMemcpyHostToDevice));
     if (w0) CU(cudaMemcpy(s->d_w0, w0, (size_t)n_existing * s->s0 * 4, cudaMemcpyHostToDevice));
-    if (rows_existing && adjU) CU(cudaMemcpy(s->d_adjU, adjU, (size_t)rows_existing * s->su * 4, cudaMemcpyHostToDevice));
-    if (rows_existing && wU) CU(cudaMemcpy(s->d_wU, wU, (size_t)rows_existing * s->su * 4, cudaMemcpyHostToDevice));
+    if (rows_existing && adjU) {
+        // fix_broken_graph (ram_hnsw.rs:52-64,118-123): a link in layer L > 0 to a node that is not in layer L is dropped
+        // (graphs written by an old version can hold them); the patched copy is made only if one is found
+        std::vector<uint32_t> fixed_adj;
+        std::vector<float> fixed_w;
+        uint64_t row = 0;
+        for (uint64_t i = 0; i < n_existing; ++i)
+            for (int layer = 1; layer <= level[i]; ++layer, ++row) {
+                const uint32_t* r0 = adjU + row * s->su;
+                bool broken = false;
+                for (int j = 0; j < s->su && r0[j] != NIL; ++j)
+                    if (r0[j] >= n_existing || level[r0[j]] < layer) { broken = true; break; }
+                if (!broken) continue;
+                if (fixed_adj.empty()) {
+                    fixed_adj.assign(adjU, adjU + rows_existing * s->su);
+                    if (wU) fixed_w.assign(wU, wU + rows_existing * s->su);
+                }
+                uint32_t* dst = fixed_adj.data() + row * s->su;
+                float* dw = wU ? fixed_w.data() + row * s->su : nullptr;
+                int kept = 0;
+                for (int j = 0; j < s->su && r0[j] != NIL; ++j)
+                    if (r0[j] < n_existing && level[r0[j]] >= layer) {
+                        dst[kept] = r0[j];
+                        if (dw) dw[kept] = wU[row * s->su + j];
+                        ++kept;
+                    }
+                for (int j = kept; j < s->su; ++j) { dst[j] = NIL; if (dw) dw[j] = 0.0f; }
+            }
+        const uint32_t* srcA = fixed_adj.empty() ? adjU : fixed_adj.data();
+        const float* srcW = fixed_adj.empty() ? wU : fixed_w.data();
+        CU(cudaMemcpy(s->d_adjU, srcA, (size_t)rows_existing * s->su * 4, cudaMemcpyHostToDevice));
+        if (wU) CU(cudaMemcpy(s->d_wU, srcW, (size_t)rows_existing * s->su * 4, cudaMemcpyHostToDevice));
+    }
     s->has_graph = true;
     if (n == n_existing) return 0;
     std::vector<uint32_t> order(n - n_existing);

@@ -199,6 +199,24 @@ def hnsw_build(vecs, sim=SIM_COSINE, M=30, M0=60, efC=100, seed=2, max_batch=1, 
     return g
 
 
+def fix_broken_links(g: Graph) -> int:
+    """ram_hnsw.rs:52-64,118-123: in every layer above 0 drop the links that point at a node not present in that layer
+    (graphs written by an old version can hold them).  Rows stay left-packed.  -> number of links removed."""
+    removed = 0
+    for node in np.nonzero(g.level > 0)[0]:
+        base = int(g.upper_off[node])
+        for layer in range(1, int(g.level[node]) + 1):
+            row, wrow = g.adjU[base + layer - 1], g.wU[base + layer - 1]
+            valid = row != NIL
+            keep = valid & (g.level[np.where(valid, row, 0)] >= layer)
+            if (keep != valid).any():
+                removed += int(valid.sum() - keep.sum())
+                ids, ws = row[keep].copy(), wrow[keep].copy()
+                row[:], wrow[:] = NIL, 0
+                row[: len(ids)], wrow[: len(ids)] = ids, ws
+    return removed
+
+
 def hnsw_extend(vecs, g0: Graph, sim=SIM_COSINE, efC=100, seed=2, max_batch=1, nthreads=1):
     """merge_indexes' fast path (segment.rs:143-167): keep g0 (the graph of the first g0.n vectors) and insert the remaining
     vectors; new levels from a fresh RNG (build.rs:36-55), entry point moved only if a higher layer appears."""
@@ -212,6 +230,7 @@ def hnsw_extend(vecs, g0: Graph, sim=SIM_COSINE, efC=100, seed=2, max_batch=1, n
     g.adj0[:n0], g.w0[:n0] = g0.adj0, g0.w0
     rows0 = int(g0.level.astype(np.int64).sum())
     g.adjU[:rows0], g.wU[:rows0] = g0.adjU[:rows0], g0.wU[:rows0]
+    fix_broken_links(g)                         # merge_indexes: index.fix_broken_graph() (segment.rs:162)
     nrm = norms(vecs, nthreads) if sim == SIM_COSINE else None
     order = np.arange(n0, n, dtype=np.uint32)
     ends, done = [], n0

@@ -310,3 +310,25 @@ def test_extend_reuses_the_existing_graph():
     # the oracle's extended graph gives 0.963 on this input, its full rebuild 0.966 (M=8, ef=64)
     assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(hi, bi)]) >= 0.95
     assert (hi >= n0).any() and (hi < n0).any()      # old and new vectors are both reachable
+
+
+def test_extend_drops_broken_upper_links():
+    """merge_indexes runs fix_broken_graph on the reused graph (segment.rs:162, ram_hnsw.rs:118-123): a layer-1 link to a
+    node that only lives in layer 0 is dropped before the new vectors are inserted."""
+    v = make_vectors(2500, 32, seed=62)
+    n0 = 2000
+    og0 = O.hnsw_build(v[:n0], M=8, M0=16, efC=40, max_batch=64, nthreads=8)
+    src = int(np.nonzero(og0.level > 0)[0][0])
+    bad = int(np.nonzero(og0.level == 0)[0][0])
+    row = og0.adjU[int(og0.upper_off[src])]
+    slot = min(int((row != O.NIL).sum()), len(row) - 1)
+    row[slot] = bad                                        # broken link (appended, or over the last edge of a full row)
+    og0.wU[int(og0.upper_off[src]), slot] = 0.25
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=8, m0=16, ef_construction=40)
+    rows0 = max(int(og0.level.astype(np.int64).sum()), 1)
+    seg.extend_hnsw(n0, og0.level, og0.adj0, og0.adjU[:rows0], og0.w0, og0.wU[:rows0], og0.entry_node, og0.entry_layer, seed=2, max_batch=64)
+    og = O.hnsw_extend(v, og0, efC=40, seed=2, max_batch=64, nthreads=8)
+    g = seg.get_graph()
+    rows = int(og.level.astype(np.int64).sum())
+    assert (g["adj0"] == og.adj0).all() and (g["adjU"][:rows] == og.adjU[:rows]).all()
+    assert bad not in g["adjU"][int(og.upper_off[src])]

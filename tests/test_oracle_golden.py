@@ -162,6 +162,16 @@ def test_fssc_dedup_and_replacement():
     assert list(addr) == [1, 2] and list(sc) == [np.float32(0.7), np.float32(0.6)]
 
 
+# ---- nidx_vector/src/hnsw/ram_hnsw.rs:173-198 test_fix_broken_links -------------------------------------------------
+def test_fix_broken_links():
+    g = O.Graph(2, 30, 60, np.array([1, 0], dtype=np.uint8))       # node 0 lives in layers 0-1, node 1 in layer 0 only
+    g.adj0[0, 0], g.adj0[1, 0] = 1, 0
+    g.w0[0, 0] = g.w0[1, 0] = 0.5
+    g.adjU[0, 0], g.wU[0, 0] = 1, 0.5                              # broken: layer-1 link to a node that is not in layer 1
+    assert O.fix_broken_links(g) == 1
+    assert (g.adjU[0] == O.NIL).all() and g.adj0[0, 0] == 1 and g.adj0[1, 0] == 0
+
+
 # ---- nidx_vector/tests/test_maxsim.rs:22-150 ------------------------------------------------------------------------
 def test_maxsim_exact_scores():
     e = np.eye(5, dtype=np.float32)
