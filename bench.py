@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--noise", type=float, default=0.15)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="N>1: two batches in flight (exchange of batch i under the search of batch i+1) instead of search -> exchange -> merge back to "
+                         "back; measured 1.5 %% SLOWER at N=2 (profiles/r01c_bench_2M_n2_pipelined.json): the in-line exchange costs 0.02 ms of a 1.63 ms step")
     return ap.parse_args()
 
 
@@ -196,7 +199,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if multi:
-        dist.init_process_group("nccl", device_id=dev)
+        try:     # the exchange kernel of batch i has to slip in between the CTAs of the search of batch i + 1
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        except Exception:
+            dist.init_process_group("nccl", device_id=dev)
 
     from nucliadb_b200 import _lib
     from nucliadb_b200.dist import ShardedSearcher
@@ -274,14 +282,26 @@ def main():
 
     sharded = ShardedSearcher(seg, nq, k, local_rank) if multi else None
 
+    pipelined = multi and args.pipeline
+
     def step(i):
         if multi:  # local search -> ONE all_gather of the [2, nq, k] partials over NVLink -> in-place merge kernel
             return sharded.search(queries[i], ef)
         return seg.search(queries[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=out)
 
+    def run_steps(first, last):
+        if not pipelined:
+            for i in range(first, last):
+                step(i)
+            return
+        for i in range(first, last):   # two batches in flight: the exchange of batch i overlaps the search of batch i + 1
+            sharded.submit(queries[i], ef)
+            if i > first:
+                sharded.collect()
+        sharded.collect()
+
     # ---- warm-up + timed region: inputs resident in HBM (value) --------------------------------------
-    for i in range(args.warmup):
-        step(i)
+    run_steps(0, args.warmup)
     torch.cuda.synchronize()
     if multi:
         dist.barrier()
@@ -292,8 +312,7 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` captures exactly the timed region
         ev0.record()
-        for i in range(args.warmup, n_batches):
-            step(i)
+        run_steps(args.warmup, n_batches)
         ev1.record()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
@@ -305,6 +324,20 @@ def main():
         ms_total = float(t.item())
         dist.barrier()
     ms_step = ms_total / args.steps
+    inline_ms = None
+    if pipelined:   # context: the same steps with search -> exchange -> merge back to back (what the pipelining removes)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for i in range(args.warmup, n_batches):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        inline_ms = float(t.item()) / args.steps
+        dist.barrier()
 
     # ---- recall + roofline accounting (separate, synchronous passes) ----------------------------------
     ids, _, _ = seg.search(queries[args.warmup], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
@@ -359,19 +392,31 @@ def main():
     host_out = (torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory())
     if multi:
         dist.barrier()
+    def to_host(r):
+        host_out[0].copy_(r[0], non_blocking=True)
+        host_out[1].copy_(r[1], non_blocking=True)
+
     with clocks:
         t0 = time.perf_counter()
-        for i in range(args.warmup, n_batches):
-            t1 = time.perf_counter()
-            if multi:  # pinned host queries -> device, sharded search + exchange + merge, merged result -> pinned host
+        if pipelined:   # pinned host queries -> device, search, exchange (overlapping the next batch's search), merge, result -> pinned host
+            for i in range(args.warmup, n_batches):
                 dq.copy_(hq[i], non_blocking=True)
-                r = sharded.search(dq, ef)
-                host_out[0].copy_(r[0], non_blocking=True)
-                host_out[1].copy_(r[1], non_blocking=True)
-                torch.cuda.synchronize()
-            else:
-                e_ids, e_sc, e_cnt = seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
-            e2e_steps.append(time.perf_counter() - t1)
+                sharded.submit(dq, ef)
+                if i > args.warmup:
+                    to_host(sharded.collect())
+            to_host(sharded.collect())
+            torch.cuda.synchronize()
+            e2e_steps = [(time.perf_counter() - t0) / args.steps]
+        else:
+            for i in range(args.warmup, n_batches):
+                t1 = time.perf_counter()
+                if multi:  # pinned host queries -> device, sharded search + exchange + merge, merged result -> pinned host
+                    dq.copy_(hq[i], non_blocking=True)
+                    to_host(sharded.search(dq, ef))
+                    torch.cuda.synchronize()
+                else:
+                    e_ids, e_sc, e_cnt = seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
+                e2e_steps.append(time.perf_counter() - t1)
         torch.cuda.synchronize()
         e2e_dt = time.perf_counter() - t0
     print(f"[bench] e2e per-step ms: min {min(e2e_steps) * 1e3:.3f} median {np.median(e2e_steps) * 1e3:.3f} max {max(e2e_steps) * 1e3:.3f}", file=sys.stderr)
@@ -450,11 +495,12 @@ def main():
         line = {
             "metric": "k-NN QPS @ recall@10", "value": qps_units, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "segments": world, "vectors_per_segment": n,
+            "config": {"workload": workload, "segments": world, "vectors_per_segment": n, "exchange": ("pipelined, 2 batches in flight" if pipelined else "in line") if multi else None,
                        "M": m, "M0": m0, "efC": args.efc, "l2": f"inputs larger than L2 ({n * d * 4 / 1e9:.1f} GB of vectors per GPU, fresh queries every step)",
                        "unit_note": "one unit = one query searched on one segment; merged_qps = user-visible queries/s over all segments",
                        "data_gen": f"latent={args.latent} noise={args.noise} normalised; queries = data point + 0.05 * unit noise"},
             "merged_qps": nq * args.steps / (ms_total * 1e-3),
+            "exchange_in_line_ms_per_step": inline_ms,
             "recall_at_10": recall,
             "ef30": ef30,
             "build": {"seconds": t_build, "vectors_per_s": n / t_build, "similarities": build_counters["similarities"], "max_batch": args.max_batch,

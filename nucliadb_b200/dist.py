@@ -33,30 +33,74 @@ def global_ids(local_ids, part, vectors_per_rank: int):
 class ShardedSearcher:
     """One rank's view of a segment-sharded index.  Buffers are allocated once: the local result is written
     straight into this rank's slot of the exchange buffer ([2, nq, k]: ids, score bits), ONE all_gather moves
-    every rank's slot, and parts_merge_kernel merges the gathered buffer in place (part_stride = 2*nq*k)."""
+    every rank's slot, and parts_merge_kernel merges the gathered buffer in place (part_stride = 2*nq*k).
 
-    def __init__(self, segment, nq, k, device, group=None):
+    ``search`` does the three steps back to back.  ``submit`` / ``collect`` pipeline them over `depth` buffer sets:
+    the all_gather of batch i runs on the process group's own stream while batch i+1 is being searched on the
+    caller's stream, and batch i is merged once its exchange has landed -- the exchange latency leaves the
+    critical path.  ``local_search`` / ``merge`` are injectable so that the CPU (gloo) tests drive the same
+    submit/collect logic without a GPU; the defaults are the C-ABI calls."""
+
+    def __init__(self, segment, nq, k, device, group=None, depth=2, local_search=None, merge=None):
         import torch
         import torch.distributed as dist
 
-        self.segment, self.nq, self.k, self.device, self.group = segment, nq, k, device, group
+        self.segment, self.nq, self.k, self.device, self.group, self.depth = segment, nq, k, device, group, depth
         self.world = dist.get_world_size(group)
-        dev = torch.device("cuda", device)
-        self.local = torch.empty((2, nq, k), dtype=torch.int32, device=dev)
-        self.counts = torch.empty((nq,), dtype=torch.int32, device=dev)
-        self.gathered = torch.empty((self.world, 2, nq, k), dtype=torch.int32, device=dev)
-        self.out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
-                    torch.empty((nq, k), dtype=torch.int32, device=dev))
+        dev = torch.device("cpu") if device == "cpu" else torch.device("cuda", device)
+        self._local_search = local_search or self._search_segment
+        self._merge = merge or self._merge_device
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                local=torch.empty((2, nq, k), dtype=torch.int32, device=dev), counts=torch.empty((nq,), dtype=torch.int32, device=dev),
+                gathered=torch.empty((self.world, 2, nq, k), dtype=torch.int32, device=dev),
+                out=(torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+                     torch.empty((nq, k), dtype=torch.int32, device=dev)), work=None))
+        self._next, self._pending = 0, []          # slot of the next submit; slots in flight, oldest first
+
+    # -- the two device steps (C ABI) -----------------------------------------------------------------------
+    def _search_segment(self, queries, ef, slot, **kw):
+        import torch
+
+        from . import _lib
+
+        self.segment.search(queries, self.k, ef=ef, method=_lib.NIDX_METHOD_HNSW,
+                            out=(slot["local"][0], slot["local"][1].view(torch.float32), slot["counts"]), **kw)
+
+    def _merge_device(self, slot):
+        import torch
+
+        from .segment import merge_topk
+
+        g = slot["gathered"]
+        return merge_topk(g[:, 0], g[:, 1].view(torch.float32), device=self.device, part_stride=2 * self.nq * self.k, out=slot["out"])
+
+    # -- pipeline -----------------------------------------------------------------------------------------------
+    def submit(self, queries, ef, **kw):
+        """Search the local segment for this batch and start the exchange; at most `depth` batches in flight."""
+        import torch.distributed as dist
+
+        if len(self._pending) == self.depth:
+            raise RuntimeError(f"{self.depth} batches already in flight: collect() first")
+        slot = self.slots[self._next]
+        self._local_search(queries, ef, slot, **kw)
+        flat = slot["gathered"].view(self.world * 2, self.nq, self.k)       # concatenation along dim 0 (the form gloo accepts too)
+        slot["work"] = dist.all_gather_into_tensor(flat, slot["local"], group=self.group, async_op=True)
+        self._pending.append(self._next)
+        self._next = (self._next + 1) % self.depth
+
+    def collect(self):
+        """-> (local ids, scores, part) of the oldest batch in flight, identical on every rank.  The tensors belong to
+        the batch's buffer set and are overwritten `depth` submits later."""
+        if not self._pending:
+            raise RuntimeError("nothing in flight")
+        slot = self.slots[self._pending.pop(0)]
+        slot["work"].wait()                  # the caller's stream waits for the exchange; the host does not (NCCL)
+        slot["work"] = None
+        return self._merge(slot)
 
     def search(self, queries, ef, **kw):
         """-> (local ids, scores, part) of the merged top-k, identical on every rank."""
-        import torch
-        import torch.distributed as dist
-
-        from . import _lib
-        from .segment import merge_topk
-
-        self.segment.search(queries, self.k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=(self.local[0], self.local[1].view(torch.float32), self.counts), **kw)
-        dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
-        g = self.gathered
-        return merge_topk(g[:, 0], g[:, 1].view(torch.float32), device=self.device, part_stride=2 * self.nq * self.k, out=self.out)
+        self.submit(queries, ef, **kw)
+        return self.collect()
