@@ -99,7 +99,9 @@ int nidx_vec_build_hnsw(nidx_vec_segment* seg, uint64_t seed, int32_t max_batch,
 /* merge_indexes' fast path (segment.rs:143-167): the first n_existing vectors of this segment already have a graph
  * (the largest input segment of a merge, without deletions) given in the flat layout below for n_existing nodes; only the
  * remaining vectors are inserted.  Levels of the new nodes come from a fresh RNG (HnswBuilder::new + initialize_graph with
- * skip_nodes = n_existing, build.rs:36-55); the entry point moves only if a higher layer appears (ram_hnsw.rs:99-107). */
+ * skip_nodes = n_existing, build.rs:36-55); the entry point moves only if a higher layer appears (ram_hnsw.rs:99-107).
+ * The edge similarities (w0, wU: the contents of hnsw.edges) are required -- the reverse-link prune ranks by them.  Links
+ * in a layer > 0 to a node that is not in that layer are dropped first (fix_broken_graph, ram_hnsw.rs:118-123). */
 int nidx_vec_extend_hnsw(nidx_vec_segment* seg, uint64_t n_existing, const uint8_t* level_existing, const uint32_t* adj0, const float* w0,
                          const uint32_t* adjU, const float* wU, uint32_t entry_node, uint32_t entry_layer, uint64_t seed, int32_t max_batch,
                          void* stream);

@@ -805,8 +805,9 @@ static void host_assign_levels(uint64_t n, int M, uint64_t seed, uint8_t* level)
 
 // Batch-synchronous insertion of order[0 .. n) into the segment's graph (which may already hold other nodes):
 // the loop of build.rs:123-166 as search / select / sort / reverse-link kernels per batch (hnsw_build.cuh).
+// entry_after_first (node, layer), if given, becomes the entry point once the first batch has been inserted.
 static int run_insertions(nidx_vec_segment* s, const std::vector<uint8_t>& level, const std::vector<uint32_t>& order, const std::vector<uint32_t>& ends,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const uint32_t* entry_after_first = nullptr) {
     uint64_t n = order.size();
     int r = 0;
     // work items (node position, layer), insertion order, layer ascending
@@ -930,6 +931,11 @@ static int run_insertions(nidx_vec_segment* s, const std::vector<uint8_t>& level
             reverse_link_kernel<<<std::min(n_rev, rev_grid), HB_THREADS, smem_rev, stream>>>(V, G, ra);
             LAUNCHED();
             begin = end;
+            if (b == 0 && entry_after_first) {   // kernel arguments travel by value: later batches start from the new entry point
+                s->entry_node = entry_after_first[0];
+                s->entry_layer = entry_after_first[1];
+                G = s->gdev();
+            }
         }
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(stream));
@@ -976,6 +982,7 @@ int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, v
 int nidx_vec_extend_hnsw(nidx_vec_segment* s, uint64_t n_existing, const uint8_t* level_existing, const uint32_t* adj0, const float* w0,
                          const uint32_t* adjU, const float* wU, uint32_t entry_node, uint32_t entry_layer, uint64_t seed, int32_t max_batch, void* stream_) {
     if (!s || !level_existing || !adj0) return fail(NIDX_EINVAL, "null argument");
+    if (!w0 || (adjU && !wU)) return fail(NIDX_EINVAL, "the existing edges' similarities are required (hnsw.edges): the reverse-link prune ranks by them");
     if (n_existing == 0 || n_existing > s->n) return fail(NIDX_EINVAL, "n_existing must be in 1..len");
     if (entry_node >= n_existing || level_existing[entry_node] < entry_layer) return fail(NIDX_EINVAL, "bad entry point");
     CU(cudaSetDevice(s->cfg.device));
@@ -986,18 +993,25 @@ int nidx_vec_extend_hnsw(nidx_vec_segment* s, uint64_t n_existing, const uint8_t
     memcpy(level.data(), level_existing, n_existing);
     for (uint64_t i = 0; i < n_existing; ++i)
         if (level[i] >= HS_MAX_LAYERS) return fail(NIDX_EINVAL, "node %llu has level %d >= %d", (unsigned long long)i, level[i], HS_MAX_LAYERS);
+    uint64_t rows_existing = 0;
+    for (uint64_t i = 0; i < n_existing; ++i) rows_existing += level[i];
+    if (rows_existing && !adjU) return fail(NIDX_EINVAL, "existing nodes have upper layers but adjU is null");
     host_assign_levels(n - n_existing, s->cfg.m, seed, level.data() + n_existing);
     int r = alloc_graph(s, level.data());
     if (r) return r;
-    uint32_t new_top = s->entry_layer, new_entry = s->entry_node;   // alloc_graph: lowest id of the global top layer
-    if (new_top <= entry_layer) { s->entry_layer = entry_layer; s->entry_node = entry_node; }
-    else { s->entry_layer = new_top; s->entry_node = new_entry; }
+    // alloc_graph left the entry point on the lowest id of the global top layer.  If that is a NEW node (the merge raises the
+    // top layer) the reference moves the entry point there before the node has a single link (update_entry_point in
+    // initialize_graph, build.rs:49-55), so every later search starts on an island and the reused graph becomes unreachable.
+    // Deliberate deviation: that node is inserted first, from the old entry point, and the entry point moves afterwards.
+    uint32_t raised[2] = {s->entry_node, s->entry_layer};
+    bool raises = raised[1] > entry_layer && raised[0] >= n_existing;
+    if (raised[1] > entry_layer && !raises) { entry_node = raised[0]; entry_layer = raised[1]; }   // the caller's entry point was below its own top layer
+    s->entry_layer = entry_layer;
+    s->entry_node = entry_node;
     // the existing nodes' rows: layer 0 rows are a prefix, and so are their upper-pool rows (offsets depend on earlier nodes only)
-    uint64_t rows_existing = 0;
-    for (uint64_t i = 0; i < n_existing; ++i) rows_existing += level[i];
     CU(cudaMemcpy(s->d_adj0, adj0, (size_t)n_existing * s->s0 * 4, cudaMemcpyHostToDevice));
-    if (w0) CU(cudaMemcpy(s->d_w0, w0, (size_t)n_existing * s->s0 * 4, cudaMemcpyHostToDevice));
-    if (rows_existing && adjU) {
+    CU(cudaMemcpy(s->d_w0, w0, (size_t)n_existing * s->s0 * 4, cudaMemcpyHostToDevice));
+    if (rows_existing) {
         // fix_broken_graph (ram_hnsw.rs:52-64,118-123): a link in layer L > 0 to a node that is not in layer L is dropped
         // (graphs written by an old version can hold them); the patched copy is made only if one is found
         std::vector<uint32_t> fixed_adj;
@@ -1032,15 +1046,19 @@ int nidx_vec_extend_hnsw(nidx_vec_segment* s, uint64_t n_existing, const uint8_t
     }
     s->has_graph = true;
     if (n == n_existing) return 0;
-    std::vector<uint32_t> order(n - n_existing);
-    for (uint64_t i = n_existing; i < n; ++i) order[i - n_existing] = (uint32_t)i;
+    std::vector<uint32_t> order;
+    order.reserve(n - n_existing);
+    if (raises) order.push_back(raised[0]);
+    for (uint64_t i = n_existing; i < n; ++i)
+        if (!raises || i != raised[0]) order.push_back((uint32_t)i);
     std::vector<uint32_t> ends;
-    for (uint64_t done = n_existing; done < n;) {
+    if (raises) ends.push_back(1);
+    for (uint64_t done = n_existing + (raises ? 1 : 0); done < n;) {
         uint64_t b = std::min<uint64_t>({(uint64_t)max_batch, std::max<uint64_t>(1, done / 16), n - done});
         done += b;
         ends.push_back((uint32_t)(done - n_existing));
     }
-    r = run_insertions(s, level, order, ends, stream);
+    r = run_insertions(s, level, order, ends, stream, raises ? raised : nullptr);
     if (r) { free_graph(s); return r; }
     return 0;
 }

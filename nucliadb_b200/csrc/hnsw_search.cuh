@@ -367,6 +367,10 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
             __syncthreads();
         }
 
+        // a node that rises above the current top layer (only on graph reuse, nidx_vec_extend_hnsw) finds nothing up there
+        if (a.mode == 1 && threadIdx.x == 0)
+            for (int layer = (int)G.entry_layer + 1; layer <= top && layer < HS_MAX_LAYERS; ++layer) a.found_count[(size_t)q * HS_MAX_LAYERS + layer] = 0;
+
         if (a.mode == 0) {
             uint32_t* oi = a.out_ids + (size_t)q * a.k;
             float* os = a.out_scores + (size_t)q * a.k;

@@ -225,24 +225,43 @@ def hnsw_extend(vecs, g0: Graph, sim=SIM_COSINE, efC=100, seed=2, max_batch=1, n
     n0 = g0.n
     level = np.concatenate([g0.level, assign_levels(n - n0, g0.M, seed)]).astype(np.uint8)
     g = Graph(n, g0.M, g0.M0, level)
-    if g.entry_layer <= g0.entry_layer:
+    raised = (g.entry_node, g.entry_layer)      # lowest id of the global top layer
+    raises = raised[1] > g0.entry_layer and raised[0] >= n0
+    if raised[1] > g0.entry_layer and not raises:
+        g.entry_node, g.entry_layer = raised    # g0's entry point was below its own top layer
+    else:
         g.entry_node, g.entry_layer = g0.entry_node, g0.entry_layer
     g.adj0[:n0], g.w0[:n0] = g0.adj0, g0.w0
     rows0 = int(g0.level.astype(np.int64).sum())
     g.adjU[:rows0], g.wU[:rows0] = g0.adjU[:rows0], g0.wU[:rows0]
     fix_broken_links(g)                         # merge_indexes: index.fix_broken_graph() (segment.rs:162)
     nrm = norms(vecs, nthreads) if sim == SIM_COSINE else None
-    order = np.arange(n0, n, dtype=np.uint32)
-    ends, done = [], n0
+    # Deviation from the reference, shared with the CUDA path (see nidx_vec_extend_hnsw): a new node that raises the top layer
+    # is inserted first, from the old entry point, and only then becomes the entry point -- the reference moves the entry point
+    # to the still unlinked node up front (build.rs:49-55), which cuts the reused graph off.
+    order = ([raised[0]] if raises else []) + [i for i in range(n0, n) if not (raises and i == raised[0])]
+    order = np.asarray(order, dtype=np.uint32)
+    ends, done = ([1] if raises else []), n0 + (1 if raises else 0)
     while done < n:
         b = min(max_batch, max(1, done // 16), n - done)
         done += b
         ends.append(done - n0)
-    ends = np.asarray(ends, dtype=np.uint32)
     counters = np.zeros(3, dtype=np.uint64)
-    lib().oracle_hnsw_build(_p(vecs), _p(nrm), C.c_uint32(n), C.c_int(d), C.c_int(d), C.c_int(sim), C.c_int(g.M), C.c_int(g.M0), C.c_int(efC), _p(g.level),
-                            C.c_uint32(g.entry_node), C.c_uint32(g.entry_layer), _p(g.adj0), _p(g.w0), _p(g.upper_off), _p(g.adjU), _p(g.wU), _p(order), _p(ends),
-                            C.c_uint32(len(ends)), C.c_int(nthreads), _p(counters))
+
+    def run(order_part, ends_part):
+        e = np.asarray(ends_part, dtype=np.uint32)
+        o = np.ascontiguousarray(order_part, dtype=np.uint32)
+        lib().oracle_hnsw_build(_p(vecs), _p(nrm), C.c_uint32(n), C.c_int(d), C.c_int(d), C.c_int(sim), C.c_int(g.M), C.c_int(g.M0), C.c_int(efC), _p(g.level),
+                                C.c_uint32(g.entry_node), C.c_uint32(g.entry_layer), _p(g.adj0), _p(g.w0), _p(g.upper_off), _p(g.adjU), _p(g.wU), _p(o), _p(e),
+                                C.c_uint32(len(e)), C.c_int(nthreads), _p(counters))
+
+    if raises:
+        run(order[:1], [1])
+        g.entry_node, g.entry_layer = raised
+        if len(order) > 1:
+            run(order[1:], [x - 1 for x in ends[1:]])
+    elif len(order):
+        run(order, ends)
     return g
 
 

@@ -332,3 +332,26 @@ def test_extend_drops_broken_upper_links():
     rows = int(og.level.astype(np.int64).sum())
     assert (g["adj0"] == og.adj0).all() and (g["adjU"][:rows] == og.adjU[:rows]).all()
     assert bad not in g["adjU"][int(og.upper_off[src])]
+
+
+def test_extend_when_a_new_node_raises_the_top_layer():
+    """A merge whose new vectors reach a layer the reused graph does not have: the raising node is inserted first from the old
+    entry point and becomes the entry point afterwards (deliberate deviation from build.rs:49-55); equal to the
+    oracle doing the same, and the reused graph stays reachable."""
+    v = make_vectors(3000, 32, seed=63)
+    n0 = 2000
+    og0 = O.hnsw_build(v[:n0], M=8, M0=16, efC=40, max_batch=64, nthreads=8)
+    seed = next(s for s in range(3, 500) if O.assign_levels(len(v) - n0, 8, s).max() > og0.entry_layer)
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=8, m0=16, ef_construction=40)
+    rows0 = max(int(og0.level.astype(np.int64).sum()), 1)
+    seg.extend_hnsw(n0, og0.level, og0.adj0, og0.adjU[:rows0], og0.w0, og0.wU[:rows0], og0.entry_node, og0.entry_layer, seed=seed, max_batch=64)
+    og = O.hnsw_extend(v, og0, efC=40, seed=seed, max_batch=64, nthreads=8)
+    g = seg.get_graph()
+    assert og.entry_layer > og0.entry_layer and og.entry_node >= n0
+    assert g["entry_node"] == og.entry_node and g["entry_layer"] == og.entry_layer and (g["level"] == og.level).all()
+    rows = int(og.level.astype(np.int64).sum())
+    assert (g["adj0"] == og.adj0).all() and (g["adjU"][:rows] == og.adjU[:rows]).all()
+    q = make_queries(v, 100)
+    bi, _, _ = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+    hi, _, _ = seg.search(q, 10, ef=64, method=_lib.NIDX_METHOD_HNSW)
+    assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(hi, bi)]) >= 0.97 and (hi < n0).any()

@@ -172,6 +172,26 @@ def test_fix_broken_links():
     assert (g.adjU[0] == O.NIL).all() and g.adj0[0, 0] == 1 and g.adj0[1, 0] == 0
 
 
+# ---- merge with graph reuse (segment.rs:143-167) when the new vectors raise the top layer ------------------------------
+def test_extend_keeps_the_reused_graph_reachable():
+    """The reference moves the entry point to the new, still unlinked top-layer node before inserting anything (build.rs:49-55);
+    restated literally that cuts the reused graph off (recall 0.31 on this input).  The oracle and the CUDA path insert that
+    node first from the old entry point instead -- the one deliberate deviation on this path."""
+    from conftest import make_queries, make_vectors
+
+    v = make_vectors(3000, 32, seed=63)
+    n0 = 2000
+    g0 = O.hnsw_build(v[:n0], M=8, M0=16, efC=40, max_batch=64, nthreads=4)
+    seed = next(s for s in range(3, 500) if O.assign_levels(len(v) - n0, 8, s).max() > g0.entry_layer)
+    g = O.hnsw_extend(v, g0, efC=40, seed=seed, max_batch=64, nthreads=4)
+    assert g.entry_layer > g0.entry_layer and g.entry_node >= n0
+    q = make_queries(v, 100)
+    bi, _, _ = O.brute_force(v, q, 10, nthreads=4)
+    hi, _, _, _ = O.hnsw_search(v, g, q, 10, 64, nthreads=4)
+    assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(hi, bi)]) >= 0.97
+    assert (hi < n0).mean() > 0.5                      # two thirds of the data are the reused segment
+
+
 # ---- nidx_vector/tests/test_maxsim.rs:22-150 ------------------------------------------------------------------------
 def test_maxsim_exact_scores():
     e = np.eye(5, dtype=np.float32)
