@@ -444,3 +444,22 @@ def rabitq_brute_force(vecs, enc, queries, k, min_score=0.0, nthreads=1):
     lib().oracle_rabitq_brute_force(_p(vecs), C.c_uint32(n), C.c_int(d), C.c_int(d), _p(enc), _p(queries), C.c_int(nq), C.c_int(d), C.c_int(k),
                                     C.c_float(min_score), _p(ids), _p(sc), _p(cnt), _p(evals), C.c_int(nthreads))
     return ids, sc, cnt, evals
+
+
+def hnsw_search_rabitq(vecs, enc, g: Graph, queries, k, min_score=0.0, with_duplicates=True, filter_bits=None, nthreads=1):
+    """hnsw/search.rs:306-383 with a SearchVector::RabitQ query (Dot similarity): the walk ranks by the RaBitQ estimate, layer 0
+    asks for min(k * 100, 2000) nodes, rerank_top re-scores with the raw vectors, closest_up_nodes works on exact similarities.
+    -> (ids, scores, count, counters[exact similarities, expansions, edges read, quantised estimates])."""
+    vecs, queries = _f32(vecs), _f32(np.atleast_2d(queries))
+    enc = np.ascontiguousarray(enc, dtype=np.uint8)
+    n, d = vecs.shape
+    nq = queries.shape[0]
+    ids = np.empty((nq, k), dtype=np.uint32)
+    sc = np.empty((nq, k), dtype=np.float32)
+    cnt = np.empty(nq, dtype=np.int32)
+    counters = np.zeros(4, dtype=np.uint64)
+    lib().oracle_hnsw_search_rabitq(_p(vecs), C.c_uint32(n), C.c_int(d), C.c_int(d), _p(enc), C.c_int(g.M), C.c_int(g.M0), _p(g.level),
+                                    C.c_uint32(g.entry_node), C.c_uint32(g.entry_layer), _p(g.adj0), _p(g.upper_off), _p(g.adjU), _p(queries),
+                                    C.c_int(nq), C.c_int(d), C.c_int(k), C.c_float(min_score), C.c_int(int(with_duplicates)), _p(filter_bits),
+                                    _p(ids), _p(sc), _p(cnt), _p(counters), C.c_int(nthreads))
+    return ids, sc, cnt, counters

@@ -243,6 +243,42 @@ void oracle_rabitq_brute_force(const float* vecs, uint32_t n, int d, int ld, con
     }
 }
 
+// HNSW search with a quantised query (search.rs:306-383, RaBitQ branch).  Dot similarity only.  counters: [exact similarities,
+// expansions, edges read, quantised estimates].
+void oracle_hnsw_search_rabitq(const float* vecs, uint32_t n, int d, int ld, const unsigned char* enc, int M, int M0, const uint8_t* level,
+                               uint32_t entry_node, uint32_t entry_layer, const uint32_t* adj0, const uint64_t* upper_off, const uint32_t* adjU,
+                               const float* queries, int nq, int qld, int k, float min_score, int with_duplicates, const uint64_t* filter_bits,
+                               uint32_t* out_ids, float* out_scores, int* out_count, uint64_t* counters, int nthreads) {
+    Data D = make_data(vecs, nullptr, n, d, ld, SIM_DOT);
+    GraphView G = make_view(n, M, M0, level, entry_node, entry_layer, const_cast<uint32_t*>(adj0), nullptr, upper_off,
+                            const_cast<uint32_t*>(adjU), nullptr);
+    int nt = nthreads > 0 ? nthreads : 1;
+    std::vector<Counters> cnts(nt);
+    std::vector<uint64_t> quant((size_t)nt * 8, 0);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int qi = 0; qi < nq; ++qi) {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        Query q{queries + (size_t)qi * qld, 0.0f};
+        NodeFilter f;
+        f.filter_bits = filter_bits; f.with_duplicates = with_duplicates != 0;
+        auto r = hnsw_search_rabitq(D, G, enc, q, (size_t)k, min_score, f, tls_scratch(), &cnts[t], &quant[(size_t)t * 8]);
+        if (r.size() > (size_t)k) r.resize(k);
+        out_count[qi] = (int)r.size();
+        for (int j = 0; j < k; ++j) {
+            out_ids[(size_t)qi * k + j] = j < (int)r.size() ? r[j].id : NIL;
+            out_scores[(size_t)qi * k + j] = j < (int)r.size() ? r[j].score : 0.0f;
+        }
+    }
+    if (counters) {
+        counters[0] = counters[1] = counters[2] = counters[3] = 0;
+        for (auto& c : cnts) { counters[0] += c.n_dist; counters[1] += c.n_expand; counters[2] += c.n_edges_read; }
+        for (int t = 0; t < nt; ++t) counters[3] += quant[(size_t)t * 8];
+    }
+}
+
 // ---- BM25 ---------------------------------------------------------------------------------------
 uint8_t oracle_fieldnorm_to_id(uint32_t v) { return fieldnorm_to_id(v); }
 uint32_t oracle_fieldnorm_id_to_value(uint32_t id) { return fieldnorm_id_to_value(id); }

@@ -151,17 +151,19 @@ static inline float sim_to(const Data& D, const Query& q, uint32_t x, Counters* 
     return similarity(D.sim, D.vec(x), D.nrm(x), q.q, q.qnorm, D.d);
 }
 
-// hnsw/search.rs:242-304.  Returns results sorted descending.
-static inline std::vector<Scored> layer_search(const Data& D, const GraphView& G, const Query& q, int layer, size_t k,
-                                               const std::vector<uint32_t>& entry_points, Scratch& sc, Counters* cnt) {
+// hnsw/search.rs:242-304.  Returns results sorted descending.  `score(x)` is Retriever::similarity_upper_bound(x, query).score:
+// the exact similarity for a dense query, the RaBitQ estimate for a quantised one (segment.rs:339-348).
+template <class ScoreFn>
+static inline std::vector<Scored> layer_search_with(uint32_t n, const GraphView& G, ScoreFn score, int layer, size_t k,
+                                                    const std::vector<uint32_t>& entry_points, Scratch& sc, Counters* cnt) {
     auto worse_first = [](const Scored& a, const Scored& b) { return better(a, b); };   // min-heap on rank
     auto better_first = [](const Scored& a, const Scored& b) { return better(b, a); };  // max-heap on rank
     std::priority_queue<Scored, std::vector<Scored>, decltype(better_first)> candidates(better_first);
     std::priority_queue<Scored, std::vector<Scored>, decltype(worse_first)> ms(worse_first);
-    sc.reset(D.n);
+    sc.reset(n);
     for (uint32_t ep : entry_points) {  // 256-261: pushed to both heaps, no k bound
         sc.test_and_set(ep);
-        Scored s{ep, sim_to(D, q, ep, cnt)};
+        Scored s{ep, score(ep)};
         candidates.push(s);
         ms.push(s);
     }
@@ -178,7 +180,7 @@ static inline std::vector<Scored> layer_search(const Data& D, const GraphView& G
             if (y == NIL) break;
             if (cnt) cnt->n_edges_read++;
             if (sc.test_and_set(y)) continue;
-            float s = sim_to(D, q, y, cnt);
+            float s = score(y);
             if (s > ws || ms.size() < k) {  // 286
                 candidates.push({y, s});
                 ms.push({y, s});
@@ -192,6 +194,10 @@ static inline std::vector<Scored> layer_search(const Data& D, const GraphView& G
     while (!ms.empty()) { out.push_back(ms.top()); ms.pop(); }
     std::reverse(out.begin(), out.end());  // into_sorted_vec of Reverse => descending
     return out;
+}
+static inline std::vector<Scored> layer_search(const Data& D, const GraphView& G, const Query& q, int layer, size_t k,
+                                               const std::vector<uint32_t>& entry_points, Scratch& sc, Counters* cnt) {
+    return layer_search_with(D.n, G, [&](uint32_t x) { return sim_to(D, q, x, cnt); }, layer, k, entry_points, sc, cnt);
 }
 
 // hnsw/search.rs:135-171 NodeFilter + 388-412 RepCounter.

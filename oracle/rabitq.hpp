@@ -6,6 +6,9 @@
 //   rabitq.rs:166-200                                     QueryVector::dot (AND + popcount per plane, weights 1, 2, 4, 8)
 //   rabitq.rs:202-218                                     QueryVector::similarity -> (estimate, error bound), EPSILON = 1.9
 //   rabitq.rs:222-244                                     rerank_top (exact re-scoring with upper-bound pruning)
+//   nidx/nidx_vector/src/hnsw/search.rs:306-383           HnswSearcher::search with a SearchVector::RabitQ query: the walk ranks by
+//                                                         the estimate, layer 0 asks for min(k * 100, 2000) nodes, rerank_top
+//                                                         re-scores them exactly, closest_up_nodes runs on exact similarities
 // Only valid for Dot similarity and dim % 64 == 0 (config.rs:170-173 quantizable_vectors).
 // `f32::dot(v, v_repr)` in encode is simsimd's dot: restated with the lane-blocked order of distance.hpp.
 #pragma once
@@ -110,6 +113,41 @@ static inline std::vector<Scored> rerank_top(const std::vector<std::pair<uint32_
     while (!best.empty()) { out.push_back(best.top()); best.pop(); }
     std::reverse(out.begin(), out.end());
     return out;
+}
+
+// hnsw/search.rs:306-383 for a quantised query (segment.rs:506-513: data store has vectors.quant and RaBitQ search is not
+// disabled).  enc: rabitq_encoded_len(d) bytes per vector.  cnt->n_dist counts EXACT similarities only; n_quant the estimates.
+static inline std::vector<Scored> hnsw_search_rabitq(const Data& D, const GraphView& G, const unsigned char* enc, const Query& q,
+                                                     size_t k_neighbours, float min_score, NodeFilter& filter, Scratch& sc, Counters* cnt,
+                                                     uint64_t* n_quant) {
+    if (k_neighbours == 0 || D.n == 0) return {};
+    RabitqQuery rq = RabitqQuery::from_vector(q.q, D.d);
+    size_t len = rabitq_encoded_len(D.d);
+    auto estimate = [&](uint32_t x) {
+        float est, err;
+        rq.similarity(enc + (size_t)x * len, &est, &err);
+        if (n_quant) ++*n_quant;
+        return est;
+    };
+    std::vector<uint32_t> eps{G.entry_node};
+    for (int layer = (int)G.entry_layer; layer > 0; --layer) {   // 321-327
+        auto r = layer_search_with(D.n, G, estimate, layer, 1, eps, sc, cnt);
+        eps.clear();
+        for (auto& s : r) eps.push_back(s.id);
+    }
+    size_t last_k = std::min(k_neighbours * RERANKING_FACTOR, RERANKING_LIMIT);   // 335-337
+    auto neighbours = layer_search_with(D.n, G, estimate, 0, last_k, eps, sc, cnt);
+    std::vector<std::pair<uint32_t, float>> cand;   // (addr, upper_bound = estimate + error), best estimate first
+    cand.reserve(neighbours.size());
+    for (auto& s : neighbours) {
+        float est, err;
+        rq.similarity(enc + (size_t)s.id * len, &est, &err);
+        cand.push_back({s.id, est + err});
+    }
+    auto reranked = rerank_top(cand, k_neighbours, min_score, [&](uint32_t v) { return sim_to(D, q, v, cnt); });   // 355-361
+    auto filtered = closest_up_nodes(D, G, q, reranked, k_neighbours, min_score, filter, sc, cnt);                  // 369-375, exact
+    std::sort(filtered.begin(), filtered.end(), better);
+    return filtered;
 }
 
 }  // namespace nidx_oracle

@@ -141,6 +141,62 @@ def test_recall_clustered_data():
     assert recall >= 0.95      # "Expected ~0.98", asserted >= 0.95 in the reference
 
 
+def test_recall_clustered_data_takes_the_rabitq_path():
+    """The same reference test, the way the reference actually runs it: for_paragraphs() is Dot and DIMENSION = 256 is a
+    multiple of 64, so the segment has vectors.quant and `_search` builds a RaBitQ query (segment.rs:506-513); with 640
+    vectors use_hnsw(.., has_rabitq = true) picks the quantised exact scan + rerank (segment.rs:581-608)."""
+    rng = np.random.default_rng(1234567890)
+    d = 256
+
+    def random_vector():
+        v = rng.uniform(-1.0, 1.0, d).astype(np.float32)
+        return (v / np.sqrt((v * v).sum())).astype(np.float32)
+
+    def nearby(base, dist):
+        v = base + random_vector() * np.float32(dist)
+        return (v / np.sqrt((v * v).sum())).astype(np.float32)
+
+    elems, center = [], random_vector()
+    for _ in range(4):
+        elems += [nearby(center, 0.01) for _ in range(80)]
+        elems += [nearby(center, 0.03) for _ in range(80)]
+        center = nearby(center, 0.1)
+    v = np.stack(elems)
+    assert not O.use_hnsw(len(v), len(v), 5, has_rabitq=True) and O.use_hnsw(len(v), len(v), 5, has_rabitq=False)
+    enc = O.rabitq_encode(v)
+    queries = np.stack([nearby(v[rng.integers(0, len(v))], 0.05) for _ in range(100)])
+    bi, _, _ = O.brute_force(v, queries, 5, sim=O.SIM_DOT, min_score=0.0)
+    ri, _, _, evals = O.rabitq_brute_force(v, enc, queries, 5, min_score=0.0)
+    assert np.mean([len(set(a) & set(b)) / 5 for a, b in zip(ri, bi)]) >= 0.95
+    assert (evals <= len(v)).all()     # candidates arrive in address order (no sort before rerank_top, segment.rs:600-608): on
+                                       # clusters this tight every upper bound beats the running k-th score, nothing is spared
+
+
+def test_hnsw_search_with_a_rabitq_query():
+    """hnsw/search.rs:306-383, RaBitQ branch (taken from ~100 k vectors up, segment.rs:626-660): walk on estimates with
+    min(k * 100, 2000) results at layer 0, exact rerank, exact closest_up_nodes.  The scores that come out are exact dots."""
+    from conftest import make_queries, make_vectors
+
+    v = make_vectors(6000, 128, seed=71)
+    g = O.hnsw_build(v, sim=O.SIM_DOT, M=16, M0=32, efC=100, max_batch=128, nthreads=4)
+    enc = O.rabitq_encode(v, nthreads=4)
+    q = make_queries(v, 64, seed=5)
+    bi, bs, _ = O.brute_force(v, q, 10, sim=O.SIM_DOT, min_score=0.0, nthreads=4)
+    ri, rs, rc, counters = O.hnsw_search_rabitq(v, enc, g, q, 10, min_score=0.0, nthreads=4)
+    assert (rc == 10).all()
+    assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ri, bi)]) >= 0.99
+    same = ri == bi
+    assert np.array_equal(rs[same], bs[same])              # reranked with the raw vectors: no estimate leaks out
+    assert (np.diff(rs, axis=1) <= 0).all()
+    assert counters[3] > 5 * counters[0]                   # far more 24-byte estimates than 512-byte exact similarities
+    # a filter is honoured by closest_up_nodes (exact phase)
+    bits = np.zeros((len(v) + 63) // 64, dtype=np.uint64)
+    keep = np.arange(0, len(v), 3)
+    np.bitwise_or.at(bits, keep // 64, np.uint64(1) << (keep % 64).astype(np.uint64))
+    fi, _, fc, _ = O.hnsw_search_rabitq(v, enc, g, q[:8], 5, min_score=0.0, filter_bits=bits, nthreads=2)
+    assert all((fi[i, : fc[i]] % 3 == 0).all() for i in range(8))
+
+
 # ---- nidx_vector/src/searcher.rs:600-688 test_vectors_deduplication + Fssc -------------------------------------
 def test_fssc_dedup_and_replacement():
     vb = np.asarray([1.0, 2.0, 3.0], np.float32).tobytes()
