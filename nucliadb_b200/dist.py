@@ -104,3 +104,50 @@ class ShardedSearcher:
         """-> (local ids, scores, part) of the merged top-k, identical on every rank."""
         self.submit(queries, ef, **kw)
         return self.collect()
+
+
+def docaddr(local_docs, part):
+    """nidx_paragraph reader.rs:310 / nidx_text reader.rs: docaddr = (segment_ord << 32) + doc; NIL stays -1."""
+    import torch
+
+    a = (part.to(torch.int64) << 32) + (local_docs.to(torch.int64) & 0xFFFFFFFF)
+    return torch.where(part.to(torch.int64) < 0, torch.full_like(a, -1), a)
+
+
+class ShardedTextSearcher(ShardedSearcher):
+    """BM25 over a doc-partitioned index: every rank holds the postings of its own documents (one tantivy segment per rank in
+    the reference's terms) scored with the statistics of the WHOLE index (`TextSegment.set_stats`; tantivy computes N, df and
+    the average length over the union of segments, nidx_tantivy/src/index_reader.rs:39-77).  Per batch: local top-k + local
+    `Count` -> one all_gather of the [2, nq, k] (doc, score bits) partials + one all_reduce of the [nq] counts -> the same
+    merge kernel as the vector path, which ranks (score desc, part asc, position asc) = merge_document_responses' comparator
+    (bm25 desc, shard, lower docaddr first; shard_merge.rs:227-231) because every part arrives sorted (score desc, doc asc)."""
+
+    def __init__(self, segment, nq, k, device, group=None, depth=2, local_search=None, merge=None):
+        import torch
+
+        super().__init__(segment, nq, k, device, group, depth, local_search, merge)
+        for slot in self.slots:
+            slot["total"] = torch.zeros((nq,), dtype=torch.int64, device=slot["local"].device)
+            slot["work_total"] = None
+
+    def _search_segment(self, queries, ef, slot, **kw):
+        import torch
+
+        terms, offsets = queries
+        self.segment.search(terms, offsets, self.k, out=(slot["local"][0], slot["local"][1].view(torch.float32), slot["counts"], slot["total"]), **kw)
+
+    def submit(self, queries, ef=None, **kw):
+        """queries = (query_terms, query_off) as for TextSegment.search; kw: mode, use_tf, min_score, after."""
+        import torch.distributed as dist
+
+        super().submit(queries, ef, **kw)
+        slot = self.slots[self._pending[-1]]
+        slot["work_total"] = dist.all_reduce(slot["total"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def collect(self):
+        """-> (local docs, scores, part, total matching documents over all parts) of the oldest batch in flight."""
+        slot = self.slots[self._pending[0]]
+        merged = super().collect()
+        slot["work_total"].wait()
+        slot["work_total"] = None
+        return (*merged, slot["total"])

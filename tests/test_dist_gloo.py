@@ -105,3 +105,39 @@ def test_world_size_2_pipelined_exchange(tmp_path):
     mp.spawn(_pipeline_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     a, b = np.load(tmp_path / "p0.npy"), np.load(tmp_path / "p1.npy")
     assert (a == b).all() and (a[:, 1] == 1).any() and (a[:, 1] == 0).any()       # same merged answer on both ranks, from both parts
+
+
+def _text_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nucliadb_b200.dist import ShardedTextSearcher, docaddr
+
+    nq, k = 5, 4
+
+    def local_search(batch, ef, slot, **kw):      # this rank's doc partition: partial top-k (score desc, doc asc) + local Count
+        rng = np.random.default_rng(7000 * rank + batch)
+        sc = np.sort(rng.integers(1, 6, (nq, k)).astype(np.float32), axis=1)[:, ::-1].copy()      # few distinct scores: ties across parts
+        docs = np.sort(rng.integers(0, 100, (nq, k)).astype(np.int32), axis=1)
+        slot["local"][0].copy_(torch.from_numpy(docs))
+        slot["local"][1].copy_(torch.from_numpy(sc.view(np.int32)))
+        slot["total"].copy_(torch.full((nq,), 10 + rank, dtype=torch.int64))
+
+    s = ShardedTextSearcher(None, nq, k, "cpu", local_search=local_search, merge=lambda slot: _np_merge(slot, nq, k))
+    docs, part, total = s.search(0, None)
+    assert (total == 10 + 11).all()                                   # Count collector: summed over the parts
+    g = s.slots[0]["gathered"].numpy()
+    for q in range(nq):                                               # merge_document_responses: bm25 desc, then shard, then lower docaddr
+        items = sorted((-float(g[r, 1].view(np.float32)[q, j]), r, int(g[r, 0][q, j])) for r in range(world) for j in range(k))[:k]
+        assert [(r, d) for _, r, d in items] == list(zip(part[q].tolist(), docs[q].tolist()))
+    addr = docaddr(torch.from_numpy(docs), torch.from_numpy(part))
+    assert ((addr >> 32).numpy() == part).all() and ((addr & 0xFFFFFFFF).numpy() == docs).all()
+    np.save(os.path.join(out_dir, f"t{rank}.npy"), addr.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_sharded_bm25(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_text_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert (np.load(tmp_path / "t0.npy") == np.load(tmp_path / "t1.npy")).all()
