@@ -96,6 +96,12 @@ const float* nidx_vec_device_vectors(const nidx_vec_segment* seg, int32_t* ld_ou
  * the frozen graph and are linked in ascending id.  seed: level RNG seed (reference uses 2). */
 int nidx_vec_build_hnsw(nidx_vec_segment* seg, uint64_t seed, int32_t max_batch, void* stream);
 
+/* The planner's cost model (use_hnsw, segment.rs:626-660): 1 if the HNSW walk is estimated cheaper than the exhaustive scan
+ * for `matching_nodes` of `total_nodes` paragraphs passing the filter.  has_rabitq = the segment carries 1-bit codes.  m = the
+ * graph's M (the reference's compile-time hnsw::M = 30).  Pure host function: needs no device.  nidx_vec_search applies it for
+ * NIDX_METHOD_AUTO. */
+int nidx_use_hnsw(uint64_t total_nodes, uint64_t matching_nodes, uint64_t top_k, int has_rabitq, int m);
+
 /* merge_indexes' fast path (segment.rs:143-167): the first n_existing vectors of this segment already have a graph
  * (the largest input segment of a merge, without deletions) given in the flat layout below for n_existing nodes; only the
  * remaining vectors are inserted.  Levels of the new nodes come from a fresh RNG (HnswBuilder::new + initialize_graph with

@@ -350,6 +350,12 @@ int nidx_vec_set_alive(nidx_vec_segment* s, const uint64_t* alive_bits, int mem)
     return 0;
 }
 
+static bool use_hnsw_cost(size_t total_nodes, size_t matching_nodes, size_t top_k, size_t M, bool has_rabitq);
+int nidx_use_hnsw(uint64_t total_nodes, uint64_t matching_nodes, uint64_t top_k, int has_rabitq, int m) {
+    if (matching_nodes == 0 || top_k == 0 || m <= 0) return 0;
+    return use_hnsw_cost((size_t)total_nodes, (size_t)matching_nodes, (size_t)top_k, (size_t)m, has_rabitq != 0) ? 1 : 0;
+}
+
 int nidx_vec_graph_dims(const nidx_vec_segment* s, int32_t* s0, int32_t* su, uint64_t* upper_rows, uint32_t* entry_node, uint32_t* entry_layer) {
     if (!s) return fail(NIDX_EINVAL, "null segment");
     if (!s->has_graph) return fail(NIDX_ESTATE, "segment has no HNSW graph");
@@ -499,13 +505,18 @@ int nidx_vec_last_kernel_ms(nidx_vec_segment* s, float* ms) {
 }
 
 // ---- search -----------------------------------------------------------------------------------
-// segment.rs:626-660 (dense f32: no RaBitQ).
-static bool use_hnsw_cost(size_t total_nodes, size_t matching_nodes, size_t top_k, size_t M) {
+// segment.rs:626-660: estimated vector evaluations of the HNSW walk vs the exhaustive scan; with RaBitQ codes a raw
+// vector costs 16 quantised ones, layer 0 is searched for RERANKING_FACTOR * 3/4 times more nodes and
+// RERANKING_FACTOR / 2 candidates per result are reranked (rabitq.rs:34).
+static bool use_hnsw_cost(size_t total_nodes, size_t matching_nodes, size_t top_k, size_t M, bool has_rabitq) {
+    const size_t RERANKING_FACTOR = 100;
+    size_t full_cost = has_rabitq ? 16 : 1, search_mult = has_rabitq ? RERANKING_FACTOR * 3 / 4 : 1, rerank_mult = has_rabitq ? RERANKING_FACTOR / 2 : 0;
     float l = logf((float)total_nodes) - 2.0f;
-    float hnsw_rq = l * l * logf((float)top_k);
-    size_t hnsw_full = top_k * M * total_nodes / std::max<size_t>(matching_nodes, 1);
-    size_t hnsw_cost = (size_t)(hnsw_rq < 0 ? 0 : hnsw_rq) + hnsw_full;
-    return hnsw_cost < matching_nodes;
+    float hnsw_rq = l * l * logf((float)top_k) * (float)search_mult;
+    size_t hnsw_full = top_k * rerank_mult + top_k * M * total_nodes / std::max<size_t>(matching_nodes, 1);
+    size_t hnsw_cost = (size_t)(hnsw_rq < 0 ? 0 : hnsw_rq) + hnsw_full * full_cost;   // `as usize` saturates a negative estimate to 0
+    size_t bf_cost = matching_nodes + top_k * rerank_mult * full_cost;
+    return hnsw_cost < bf_cost;
 }
 
 __global__ void and_bits_kernel(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t words, unsigned long long* count) {
@@ -625,7 +636,13 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
     if (method == NIDX_METHOD_AUTO) {
         if (!s->has_graph) method = NIDX_METHOD_BRUTE;
         else if (matching == 0 && p->filter_bits) method = NIDX_METHOD_BRUTE;
-        else method = use_hnsw_cost(s->n_par, matching, (size_t)k, (size_t)s->cfg.m) ? NIDX_METHOD_HNSW : NIDX_METHOD_BRUTE;
+        else {
+            // the quantised scan serves single-vector Dot segments that carry codes (segment.rs:506-513); the HNSW walk itself is the
+            // dense one either way (the quantised walk is not implemented: results are at least as exact)
+            bool quant_ok = s->d_quant && !s->d_par_first && k <= 1024 && s->cfg.similarity == NIDX_SIM_DOT;
+            if (use_hnsw_cost(s->n_par, matching, (size_t)k, (size_t)s->cfg.m, quant_ok)) method = NIDX_METHOD_HNSW;
+            else method = quant_ok ? NIDX_METHOD_BRUTE_RABITQ : NIDX_METHOD_BRUTE;
+        }
     }
     if (method == NIDX_METHOD_HNSW && !s->has_graph) return fail(NIDX_ESTATE, "HNSW search requested but the segment has no graph");
 

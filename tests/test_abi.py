@@ -49,3 +49,23 @@ def test_no_device_fails_loudly():
     from nucliadb_b200.segment import VectorSegment
     with pytest.raises(_lib.NidxError):
         VectorSegment.create(v, 8)
+
+
+def test_cost_model_is_a_host_function_equal_to_the_oracle():
+    """nidx_use_hnsw (segment.rs:626-660) needs no device; same decisions as the oracle's restatement on a grid, with and
+    without RaBitQ, including SURVEY F6's known point (100 k unfiltered vectors, k = 10 => HNSW)."""
+    import ctypes as C
+
+    import oracle as O
+
+    L = _lib.load()
+    L.nidx_use_hnsw.restype = C.c_int
+    call = lambda t, mt, k, rq, m=30: bool(L.nidx_use_hnsw(C.c_uint64(t), C.c_uint64(mt), C.c_uint64(k), C.c_int(int(rq)), C.c_int(m)))
+    assert call(100_000, 100_000, 10, False) and not call(100_000, 500, 10, False)
+    for total in (1, 7, 640, 5_000, 100_000, 10_000_000):
+        for frac in (1.0, 0.3, 0.01, 0.0001):
+            matching = max(1, int(total * frac))
+            for k in (1, 5, 10, 100):
+                for rq in (False, True):
+                    for m in (16, 30):
+                        assert call(total, matching, k, rq, m) == O.use_hnsw(total, matching, k, has_rabitq=rq, M=m), (total, matching, k, rq, m)
