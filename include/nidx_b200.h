@@ -96,6 +96,11 @@ const float* nidx_vec_device_vectors(const nidx_vec_segment* seg, int32_t* ld_ou
  * the frozen graph and are linked in ascending id.  seed: level RNG seed (reference uses 2). */
 int nidx_vec_build_hnsw(nidx_vec_segment* seg, uint64_t seed, int32_t max_batch, void* stream);
 
+/* The top layer of every node as HnswBuilder::initialize_graph draws them (build.rs:40,49-55,97-101: SmallRng seeded with
+ * `seed` (the reference uses 2), level = round(-ln(u) / ln(M))), capped at the library's layer limit.  nidx_vec_build_hnsw uses
+ * exactly these.  Pure host function: needs no device. */
+int nidx_hnsw_levels(uint64_t n, int32_t m, uint64_t seed, uint8_t* out_level);
+
 /* The planner's cost model (use_hnsw, segment.rs:626-660): 1 if the HNSW walk is estimated cheaper than the exhaustive scan
  * for `matching_nodes` of `total_nodes` paragraphs passing the filter.  has_rabitq = the segment carries 1-bit codes.  m = the
  * graph's M (the reference's compile-time hnsw::M = 30).  Pure host function: needs no device.  nidx_vec_search applies it for

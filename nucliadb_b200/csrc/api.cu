@@ -964,6 +964,13 @@ static int run_insertions(nidx_vec_segment* s, const std::vector<uint8_t>& level
 
 extern "C" {
 
+int nidx_hnsw_levels(uint64_t n, int32_t m, uint64_t seed, uint8_t* out_level) {
+    if (!out_level && n) return fail(NIDX_EINVAL, "null argument");
+    if (m < 2) return fail(NIDX_EINVAL, "M must be at least 2");
+    host_assign_levels(n, m, seed, out_level);
+    return 0;
+}
+
 int nidx_vec_build_hnsw(nidx_vec_segment* s, uint64_t seed, int32_t max_batch, void* stream_) {
     if (!s) return fail(NIDX_EINVAL, "null segment");
     CU(cudaSetDevice(s->cfg.device));
