@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import os
 import uuid as _uuid
 from dataclasses import dataclass, field
 from typing import Iterable, Optional, Sequence, Union
@@ -220,6 +221,40 @@ class OpenSegment:
         seg.host_vectors = arr
         if build_graph and len(arr):
             check(L.nidx_vec_build_hnsw(h, C.c_uint64(seed), C.c_int32(max_batch), None))
+        return seg
+
+    def save(self, directory: str):
+        """Write the segment in the reference's data-store-v2 layout: vectors.bin, hnsw.graph, hnsw.edges (the library,
+        segment_io.hpp) and paragraphs.bin / paragraphs.pos (paragraph_store.py).  The inverted indexes (index.map, field.fst,
+        label.fst) are not written: `open` rebuilds them from the paragraphs, as the reference's `build_indexes` does
+        (segment.rs:183)."""
+        from . import paragraph_store as PS
+
+        check(_lib.load().nidx_vec_save(self._h, directory.encode()))
+        PS.write_paragraphs(directory, ((self.keys[p], self.labels[p], self.metadata[p], int(self.first_vec[p]), int(self.first_vec[p + 1] - self.first_vec[p]))
+                                        for p in range(self.records)))
+
+    @classmethod
+    def open(cls, config: VectorConfig, directory: str, tags=frozenset()):
+        """segment::open (segment.rs:39-90) for a data-store-v2 directory: vectors and graph go to the device, ids / labels /
+        metadata of the paragraphs stay on the host."""
+        from . import paragraph_store as PS
+
+        L = _lib.require_device()
+        paragraphs = PS.read_paragraphs(directory)
+        first = [p[3] for p in paragraphs] + [paragraphs[-1][3] + paragraphs[-1][4] if paragraphs else 0]
+        for i, p in enumerate(paragraphs):
+            if p[3] + p[4] != first[i + 1]:
+                raise NidxError(-1, f"paragraph {i} does not own a contiguous vector range")
+        record = np.dtype([("vector", np.float32, (config.dimension,)), ("paragraph", np.uint32)])
+        stored = np.fromfile(os.path.join(directory, "vectors.bin"), dtype=record)
+        if len(stored) != first[-1]:
+            raise NidxError(-1, f"vectors.bin holds {len(stored)} vectors, paragraphs.bin accounts for {first[-1]}")
+        h = C.c_void_p()
+        cfg = config._c()
+        check(L.nidx_vec_open(C.byref(cfg), directory.encode(), C.byref(h)))
+        seg = cls(config, h, [p[0] for p in paragraphs], [p[1] for p in paragraphs], [p[2] for p in paragraphs], first, tags)
+        seg.host_vectors = np.ascontiguousarray(stored["vector"])
         return seg
 
     def close(self):

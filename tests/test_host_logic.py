@@ -1,8 +1,10 @@
 """Host-side logic of the reference-interface mirror (no GPU): field keys, label filters, Fssc, BM25
 host helpers, use of the oracle only as the checker."""
+import os
 import uuid
 
 import numpy as np
+import pytest
 
 import oracle as O
 from nucliadb_b200 import text as T
@@ -66,3 +68,33 @@ def test_fieldnorm_code_matches_oracle_table():
 def test_tokenizer_is_lowercase_alnum():
     assert T.tokenize("Hello, World! it's 42") == ["hello", "world", "it", "s", "42"]
     assert T.tokenize("x" * 41) == []
+
+
+# ---- paragraphs.bin / paragraphs.pos (data_store/v2/paragraph_store.rs; bincode 2 standard config, utils.rs:25-28) ---------
+def test_bincode_varint_boundaries():
+    from nucliadb_b200 import paragraph_store as PS
+
+    cases = {0: b"\x00", 250: b"\xfa", 251: b"\xfb\xfb\x00", 65535: b"\xfb\xff\xff", 65536: b"\xfc\x00\x00\x01\x00",
+             2 ** 32 - 1: b"\xfc\xff\xff\xff\xff", 2 ** 32: b"\xfd\x00\x00\x00\x00\x01\x00\x00\x00"}
+    for value, enc in cases.items():
+        assert PS.encode_varint(value) == enc and PS.decode_varint(enc, 0) == (value, len(enc))
+
+
+def test_stored_paragraph_bytes_and_store_round_trip(tmp_path):
+    from nucliadb_b200 import paragraph_store as PS
+
+    # StoredParagraph {key: "k", labels: ["/l/a"], metadata: [1, 2], first_vector: 300, num_vectors: 1}, hand-encoded
+    want = b"\x01k" + b"\x01" + b"\x04/l/a" + b"\x02\x01\x02" + b"\xfb\x2c\x01" + b"\x01"
+    assert PS.encode_paragraph("k", ["/l/a"], b"\x01\x02", 300, 1) == want
+    assert PS.decode_paragraph(want) == (("k", ["/l/a"], b"\x01\x02", 300, 1), len(want))
+    paragraphs = [(f"9cb39c75f8d9498d8f82d92b173011f5/f/field/{i}-{i + 1}", [f"/l/set/{j}" for j in range(i % 3)], None if i % 2 else bytes(range(i % 7)), 2 * i, 2)
+                  for i in range(300)]
+    paragraphs.append(("x" * 300, ["y" * 70000], b"z" * 260, 2 ** 31, 7))       # lengths and integers past one byte / two bytes
+    assert PS.write_paragraphs(str(tmp_path), paragraphs) == 301
+    back = PS.read_paragraphs(str(tmp_path))
+    assert back == [(k, list(l), (m or None), f, n) for k, l, m, f, n in paragraphs]
+    assert os.path.getsize(tmp_path / "paragraphs.pos") == 301 * 4                # stored_elements = len / 4 (paragraph_store.rs:109)
+    with open(tmp_path / "paragraphs.pos", "ab") as f:
+        f.write(b"\xff\xff\xff\x7f")
+    with pytest.raises(ValueError):
+        PS.read_paragraphs(str(tmp_path))
