@@ -1,13 +1,18 @@
 """The CUDA path, through the C ABI, against the committed fixtures of tests/golden/ (frozen oracle outputs, see
 tests/golden/make_golden.py): ids, edges and vector scores bit-exact, BM25 scores within the stated 1e-5.  Independent of what
 is compiled on the GPU box.  (Sorted last on purpose: the live oracle comparisons of test_gpu_*.py run first.)"""
+import os
+
 import numpy as np
 import pytest
 
 import oracle as O
 from test_golden_fixtures import BM25_CASES, load, postings_of
 
-pytestmark = pytest.mark.gpu
+# Written after this round's GPU budget was spent: they have passed against an oracle-backed stand-in of the device API on CPU
+# but have not run on hardware yet, so they are opt-in until they have (set NIDX_B200_UNVERIFIED_GPU_TESTS=1).
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("NIDX_B200_UNVERIFIED_GPU_TESTS") != "1",
+                                                  reason="not yet run on a GPU box; set NIDX_B200_UNVERIFIED_GPU_TESTS=1")]
 
 
 def test_cuda_path_reproduces_the_vector_fixture():
