@@ -15,6 +15,7 @@
 
 #include "../../include/nidx_b200.h"
 #include "bm25.cuh"
+#include "bm25_w.cuh"
 #include "common.cuh"
 #include "hnsw_build.cuh"
 #include "hnsw_search.cuh"
@@ -1354,7 +1355,18 @@ int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint
     // Measured SLOWER than the flattened kernel on the 5M-doc / 50-term workload (97k vs 169k QPS: 12-posting slices
     // leave 60 % of the lanes idle and serialise a warp's terms), so it stays an experiment.
     const char* bm_env = getenv("NIDX_B200_BM25");
-    if (max_terms <= BM_TM_TERMS && bm_env && !strcmp(bm_env, "tm")) {
+    // NIDX_B200_BM25=w128 | w256: the warp-chunked variant (bm25_w.cuh: one term search per lane and round, ratio table for tf == 1),
+    // bit-identical arithmetic; not measured yet, so not the default.
+    if (bm_env && (!strcmp(bm_env, "w128") || !strcmp(bm_env, "w256"))) {
+        size_t smem_w = bw_smem_bytes(cap, p->mode == NIDX_BM25_AND);
+        if (!strcmp(bm_env, "w128")) {
+            CU(cudaFuncSetAttribute(bm25_w_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            bm25_w_kernel<128, 4><<<nq, 128, smem_w, stream>>>(T, a);
+        } else {
+            CU(cudaFuncSetAttribute(bm25_w_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            bm25_w_kernel<256, 2><<<nq, 256, smem_w, stream>>>(T, a);
+        }
+    } else if (max_terms <= BM_TM_TERMS && bm_env && !strcmp(bm_env, "tm")) {
         size_t smem_tm = bm_tm_smem_bytes(cap, p->mode == NIDX_BM25_AND);
         CU(cudaFuncSetAttribute(bm25_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm));
         bm25_tm_kernel<<<nq, BM_THREADS, smem_tm, stream>>>(T, a);
