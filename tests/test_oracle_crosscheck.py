@@ -91,3 +91,107 @@ def test_built_graph_invariants():
                 assert abs(float(wt) - O.cosine(v[node], v[int(t)])) < 1e-6
     deg0 = (g.adj0 != O.NIL).sum(1)
     assert deg0.min() >= 1                                                          # nobody is left without a link
+
+
+# ---- a literal Python transcription of hnsw/search.rs (heapq, sets) against the oracle's C++ walk ---------------------------------
+import heapq
+
+
+class _Key:
+    """Ordering of Cnx / CnxWithBound (search.rs:87-123: f32 total_cmp on the score) with the oracle's documented tie rule: of two
+    equal scores the lower id ranks higher (the reference leaves ties to BinaryHeap / sort_unstable)."""
+    __slots__ = ("id", "score")
+
+    def __init__(self, id, score):
+        self.id, self.score = int(id), float(score)
+
+    def rank(self):
+        return (self.score, -self.id)
+
+    def __lt__(self, other):
+        return self.rank() < other.rank()
+
+
+class _Max(_Key):                      # heapq is a min-heap: invert for BinaryHeap<Cnx>
+    def __lt__(self, other):
+        return self.rank() > other.rank()
+
+
+def py_layer_search(sim, edges, k, entry_points):
+    """search.rs:242-304."""
+    visited = set()
+    candidates, ms = [], []            # BinaryHeap<CnxWithBound> (max), BinaryHeap<Reverse<CnxWithBound>> (min)
+    for ep in entry_points:
+        visited.add(ep)
+        s = sim(ep)
+        heapq.heappush(candidates, _Max(ep, s))
+        heapq.heappush(ms, _Key(ep, s))
+    while candidates:
+        c = heapq.heappop(candidates)
+        ws = ms[0].score
+        if c.score < ws:
+            break
+        for y in edges(c.id):
+            if y not in visited:
+                visited.add(y)
+                s = sim(y)
+                if s > ws or len(ms) < k:
+                    heapq.heappush(candidates, _Max(y, s))
+                    heapq.heappush(ms, _Key(y, s))
+                    if len(ms) > k:
+                        heapq.heappop(ms)
+                    ws = ms[0].score
+    return sorted(ms, key=lambda x: x.rank(), reverse=True)
+
+
+def py_search(sim, g, vecs, k, ef, min_score, filter_bits, with_duplicates):
+    """search.rs:306-383 (dense query) + closest_up_nodes 188-240 + NodeFilter::passes 147-170."""
+    eps = [g.entry_node]
+    for layer in range(g.entry_layer, 0, -1):
+        eps = [x.id for x in py_layer_search(sim, lambda n, l=layer: g.edges(n, l), 1, eps)]
+    neighbours = py_layer_search(sim, lambda n: g.edges(n, 0), max(k, ef), eps)
+    results, accepted = [], []
+    visited = {x.id for x in neighbours}
+    candidates = sorted(neighbours, key=lambda x: x.rank())          # ascending; pop() takes the best
+    while candidates:
+        c = candidates.pop()
+        if c.score < min_score:
+            break
+        passes = not np.isnan(c.score)
+        if passes and filter_bits is not None:
+            passes = bool((int(filter_bits[c.id >> 6]) >> (c.id & 63)) & 1)
+        if passes and not with_duplicates:
+            passes = not any(vecs[a].tobytes() == vecs[c.id].tobytes() for a in accepted)
+            if passes:
+                accepted.append(c.id)
+        if passes:
+            results.append(c)
+        if len(results) == k:
+            break
+        for y in g.edges(c.id, 0):
+            if y not in visited:
+                visited.add(y)
+                s = sim(y)
+                if s >= min_score:
+                    candidates.append(_Key(y, s))
+        candidates.sort(key=lambda x: x.rank())
+    return sorted(results, key=lambda x: x.rank(), reverse=True)
+
+
+def test_oracle_walk_equals_the_python_transcription():
+    v = make_vectors(1500, 32, seed=36)
+    v[900:904] = v[20:24]                                            # exact duplicates
+    g = O.hnsw_build(v, M=6, M0=12, efC=30, max_batch=8, nthreads=4)
+    q = np.concatenate([make_queries(v, 12, seed=37), v[20:22]])
+    keep = np.random.default_rng(5).random(len(v)) < 0.5
+    words = np.zeros((len(v) + 63) // 64 * 8, dtype=np.uint8)
+    pb = np.packbits(keep, bitorder="little")
+    words[: len(pb)] = pb
+    bits = words.view(np.uint64)
+    for filter_bits, with_duplicates, min_score, ef in ((None, True, -1.0, 20), (bits, False, 0.0, 20), (bits, True, 0.2, 5)):
+        ids, sc, cnt, _ = O.hnsw_search(v, g, q, 7, ef, min_score=min_score, with_duplicates=with_duplicates, filter_bits=filter_bits)
+        for qi in range(len(q)):
+            want = py_search(lambda x: O.cosine(v[x], q[qi]), g, v, 7, ef, min_score, filter_bits, with_duplicates)
+            assert cnt[qi] == len(want)
+            assert ids[qi, : cnt[qi]].tolist() == [x.id for x in want]
+            assert sc[qi, : cnt[qi]].tolist() == [np.float32(x.score) for x in want]
