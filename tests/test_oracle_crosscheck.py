@@ -195,3 +195,55 @@ def test_oracle_walk_equals_the_python_transcription():
             assert cnt[qi] == len(want)
             assert ids[qi, : cnt[qi]].tolist() == [x.id for x in want]
             assert sc[qi, : cnt[qi]].tolist() == [np.float32(x.score) for x in want]
+
+
+def py_select_neighbours(pair_sim, k, candidates):
+    """build.rs:57-95.  candidates: [(id, similarity to the new node)] in the given order."""
+    results, discarded = [], []
+    for x, s in candidates:
+        if len(results) == k:
+            break
+        if all(s > pair_sim(x, y) for y, _ in results):
+            results.append((x, s))
+        else:
+            heapq.heappush(discarded, _Max(x, s))
+    if len(results) < k:
+        while len(results) < k and discarded:
+            d = heapq.heappop(discarded)
+            results.append((d.id, d.score))
+        results.sort(key=lambda t: (-t[1], t[0]))
+    return results
+
+
+def test_oracle_build_equals_the_python_transcription():
+    """build.rs:104-166 one node at a time (the reference with a single rayon thread, in the oracle's insertion order: entry point
+    first, then ascending id) against hnsw_build(max_batch = 1), edge for edge."""
+    n, M, M0, efC = 260, 4, 8, 12
+    v = make_vectors(n, 24, seed=38)
+    g = O.hnsw_build(v, M=M, M0=M0, efC=efC, max_batch=1)
+    level = O.assign_levels(n, M, 2)
+    top = int(level.max())
+    entry = int(np.nonzero(level == top)[0][0])
+    out = [{int(i): [] for i in np.nonzero(level >= l)[0]} for l in range(top + 1)]      # RAMLayer.out per layer
+    pair = lambda a, b: O.cosine(v[a], v[b])
+    prune_m = lambda m: m * 95 // 100                                                     # params.rs:29-31
+    for x in [entry] + [i for i in range(n) if i != entry]:
+        eps, found = [entry], {}
+        for l in range(top, -1, -1):                                                       # insert(): top-down search
+            in_layer = l <= level[x]
+            res = py_layer_search(lambda y: pair(y, x), lambda node, l=l: [t for t, _ in out[l][node]], efC if in_layer else 1, eps)
+            eps = [r.id for r in res]
+            if in_layer:
+                found[l] = [(r.id, r.score) for r in res]
+        for l in range(0, int(level[x]) + 1):                                              # then link bottom-up (layer_insert)
+            mmax = M0 if l == 0 else M
+            neighbours = py_select_neighbours(pair, M, found[l])
+            out[l][x] = list(neighbours)
+            for y, s in neighbours:
+                out[l][y].append((x, s))
+                if len(out[l][y]) > mmax:
+                    out[l][y] = py_select_neighbours(pair, prune_m(mmax), out[l][y])
+    assert g.entry_node == entry and g.entry_layer == top
+    for l in range(top + 1):
+        for node, edges in out[l].items():
+            assert g.edges(node, l).tolist() == [t for t, _ in edges], (l, node)
