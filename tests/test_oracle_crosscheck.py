@@ -247,3 +247,40 @@ def test_oracle_build_equals_the_python_transcription():
     for l in range(top + 1):
         for node, edges in out[l].items():
             assert g.edges(node, l).tolist() == [t for t, _ in edges], (l, node)
+
+
+def test_rabitq_oracle_equals_a_numpy_transcription():
+    """rabitq.rs:75-106 (encode), 124-157 (query planes), 166-218 (dot, similarity) in numpy float32, operation by operation."""
+    f32 = np.float32
+    d = 192
+    rng = np.random.default_rng(39)
+    v = rng.standard_normal((50, d)).astype(f32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    v[3, :5] = 0.0
+    q = rng.standard_normal((4, d)).astype(f32)
+    enc = O.rabitq_encode(v)
+    assert enc.shape == (50, d // 8 + 8)
+    bits = np.unpackbits(enc[:, 8:], axis=1, bitorder="little")[:, :d].astype(bool)          # u64 LE words, bit i % 64 of word i / 64
+    assert (bits == (v > 0)).all()                                                            # `> 0.0`: zero goes to the negative side
+    assert (enc[:, 4:8].copy().view(np.uint32)[:, 0] == (v > 0).sum(1)).all()                 # sum_bits
+    dqo = enc[:, 0:4].copy().view(f32)[:, 0]                                                  # dot(v, sign(v) / sqrt(d))
+    assert np.abs(dqo - np.abs(v).sum(1, dtype=np.float64) / np.sqrt(d)).max() < 1e-6
+    for qi in range(len(q)):
+        low, hi = q[qi].min(), f32(q[qi].max() + f32(0.00001))
+        delta = f32(f32(hi - low) / f32(16.0))
+        wq = (f32(q[qi] - low) / delta).astype(np.uint64)
+        planes, olow, odelta, osum = O.rabitq_query(q[qi])
+        assert olow == low and odelta == delta and osum == int(wq.sum())
+        for b in range(4):
+            want = np.packbits(((wq >> np.uint64(b)) & np.uint64(1)).astype(np.uint8), bitorder="little").view(np.uint64)
+            assert (planes[b] == want).all()
+        est, err = O.rabitq_estimate(enc, d, q[qi : qi + 1])
+        root_dim = f32(np.sqrt(f32(d)))
+        for i in range(len(v)):
+            dot = f32(int((wq * bits[i]).sum()))                                              # d0 + 2 d1 + 4 d2 + 8 d3
+            sum_bits = f32(int(bits[i].sum()))
+            dqq = f32(f32(f32(f32(f32(2.0) * delta) / root_dim) * dot) + f32(f32(f32(f32(2.0) * low) * sum_bits) / root_dim))
+            dqq = f32(f32(dqq - f32(f32(delta * f32(int(wq.sum()))) / root_dim)) - f32(low * root_dim))
+            assert est[0, i] == f32(dqq / dqo[i])
+            d2 = f32(dqo[i] * dqo[i])
+            assert err[0, i] == f32(f32(f32(np.sqrt(f32(f32(f32(1.0) - d2) / d2))) * f32(1.9)) / root_dim)
