@@ -284,3 +284,32 @@ def test_rabitq_oracle_equals_a_numpy_transcription():
             assert est[0, i] == f32(dqq / dqo[i])
             d2 = f32(dqo[i] * dqo[i])
             assert err[0, i] == f32(f32(f32(np.sqrt(f32(f32(f32(1.0) - d2) / d2))) * f32(1.9)) / root_dim)
+
+
+def test_rabitq_scan_and_rerank_equal_a_python_transcription():
+    """segment.rs:581-608 + rabitq.rs:222-244: estimate every vector, keep upper_bound >= min_score, then rerank_top in address
+    order (exact similarity only when the bound could still beat the k-th best)."""
+    d, k = 128, 5
+    v = make_vectors(400, d, seed=40)
+    q = make_queries(v, 6, seed=41)
+    enc = O.rabitq_encode(v)
+    for min_score in (0.0, 0.4):
+        ids, sc, cnt, evals = O.rabitq_brute_force(v, enc, q, k, min_score=min_score)
+        est, err = O.rabitq_estimate(enc, d, q)
+        for qi in range(len(q)):
+            best, best_k, n_exact = [], 0.0, 0                       # BinaryHeap<Reverse<Cnx>> as a min-heap of (score, -id)
+            for addr in range(len(v)):
+                upper = np.float32(est[qi, addr] + err[qi, addr])
+                if not upper >= np.float32(min_score):
+                    continue
+                if len(best) < k or best_k < upper:
+                    real = O.dot(v[addr], q[qi])
+                    n_exact += 1
+                    if real >= min_score and (len(best) < k or best_k < real):
+                        heapq.heappush(best, _Key(addr, real))
+                        if len(best) > k:
+                            heapq.heappop(best)
+                        best_k = best[0].score
+            want = sorted(best, key=lambda x: x.rank(), reverse=True)
+            assert cnt[qi] == len(want) and evals[qi] == n_exact
+            assert ids[qi, : cnt[qi]].tolist() == [x.id for x in want] and sc[qi, : cnt[qi]].tolist() == [np.float32(x.score) for x in want]
