@@ -34,12 +34,12 @@ namespace nidx_oracle {
 
 enum Similarity : int { SIM_DOT = 0, SIM_COSINE = 1 };
 
+// Lane 0's value of the xor butterfly (v[l] += v[l ^ off] for off = 16, 8, 4, 2, 1).  Lane 0 only ever consumes lanes below
+// `off`, whose values are v[l] + v[l + off] with the operands in that order: the halving tree below is the same arithmetic
+// with 31 additions instead of 160.
 static inline float butterfly32(float v[32]) {
-    for (int off = 16; off >= 1; off >>= 1) {
-        float t[32];
-        for (int l = 0; l < 32; ++l) t[l] = v[l] + v[l ^ off];
-        std::memcpy(v, t, sizeof(t));
-    }
+    for (int off = 16; off >= 1; off >>= 1)
+        for (int l = 0; l < off; ++l) v[l] = v[l] + v[l + off];
     return v[0];
 }
 
