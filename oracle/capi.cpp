@@ -301,7 +301,9 @@ void oracle_bm25_search(uint32_t n_docs, uint32_t n_terms, const uint64_t* term_
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1)
     for (int qi = 0; qi < nq; ++qi) {
         uint64_t total = 0;
-        auto r = bm25_search(P, S, query_terms + query_off[qi], (int)(query_off[qi + 1] - query_off[qi]), mode, use_tf != 0, (size_t)k, &total);
+        static thread_local Bm25Scratch scratch;
+        auto r = bm25_search(P, S, query_terms + query_off[qi], (int)(query_off[qi + 1] - query_off[qi]), mode, use_tf != 0, (size_t)k, &total,
+                             scratch);
         out_count[qi] = (int)r.size();
         if (out_total) out_total[qi] = total;
         for (int j = 0; j < k; ++j) {
