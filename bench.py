@@ -442,7 +442,7 @@ def main():
                 errors.append(e)
 
         def warm(j):
-            for i in range(j, max(args.warmup, 2), 2):
+            for i in range(j, min(max(args.warmup, 2), n_batches), 2):
                 seg.search(hq_np[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, stream=streams[j].cuda_stream)
 
         threads = [threading.Thread(target=warm, args=(j,)) for j in range(2)]   # second workspace allocated outside the timed region
