@@ -243,8 +243,9 @@ def bench_bm25(args):
         for _ in range(args.steps):
             docs, sc, cnt, tot = ts.search(qt_h, qo_h, k, mode=mode, use_tf=use_tf)
         e2e = nq * args.steps / (time.perf_counter() - t0)
-        # oracle on a bounded sample
-        ns = 64
+        # oracle on a bounded sample (every thread's scratch is allocated by an untimed warm-up call first)
+        ns = min(nq, 1024)
+        O.bm25_search(P, [list(x) for x in queries[: 4 * effective_cores()]], k, mode=mode, use_tf=use_tf, nthreads=effective_cores())
         t0 = time.perf_counter()
         od, osc, oc, otot = O.bm25_search(P, [list(x) for x in queries[:ns]], k, mode=mode, use_tf=use_tf, nthreads=effective_cores())
         cpu_dt = time.perf_counter() - t0
