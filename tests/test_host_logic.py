@@ -98,3 +98,49 @@ def test_stored_paragraph_bytes_and_store_round_trip(tmp_path):
         f.write(b"\xff\xff\xff\x7f")
     with pytest.raises(ValueError):
         PS.read_paragraphs(str(tmp_path))
+
+
+# ---- the posting-to-lane assignment of the warp-chunked BM25 kernel variants (csrc/bm25_w.cuh), restated in Python -----------------
+def test_warp_chunked_assignment_covers_every_posting_once():
+    """bm25_w_kernel<THREADS, ROUND>: in the round starting at flattened index `base`, warp w / lane l / slot u handles
+    i = base + w * (ROUND * 32) + u * 32 + l; the term is found by one binary search for slot 0 (`locate`) and by walking forward
+    for the next slots (`walk`).  Every flattened posting of a tile must be visited exactly once and land on the (term, offset)
+    the per-posting binary search of bm25_kernel gives."""
+    rng = np.random.default_rng(12)
+
+    def locate(pre, nt, i):                       # last term with pre[t] <= i
+        lo, r = 0, nt - 1
+        while lo < r:
+            m = (lo + r + 1) >> 1
+            if pre[m] <= i:
+                lo = m
+            else:
+                r = m - 1
+        return lo
+
+    for threads, rounds in ((128, 4), (256, 2)):
+        chunk, warps = rounds * 32, threads // 32
+        for trial in range(40):
+            nt = int(rng.integers(1, 129))
+            counts = rng.integers(0, 40, nt) * (rng.random(nt) < 0.7)          # many empty slices, as in a real tile
+            if trial == 0:
+                counts[:] = 0
+            pre = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+            total = int(counts.sum())
+            seen = np.zeros(total, dtype=np.int64)
+            for base in range(0, max(total, 1), threads * rounds):
+                for w in range(warps):
+                    for lane in range(32):
+                        i0 = base + w * chunk + lane
+                        if i0 >= total:
+                            continue
+                        l = locate(pre, nt, i0)
+                        for u in range(rounds):
+                            i = i0 + u * 32
+                            if i >= total:
+                                break
+                            while l + 1 < nt and pre[l + 1] <= i:   # walk
+                                l += 1
+                            assert l == locate(pre, nt, i) and 0 <= i - pre[l] < counts[l]
+                            seen[i] += 1
+            assert (seen == 1).all()
