@@ -486,8 +486,9 @@ def main():
         sample_q = np.concatenate([hq0] * reps)[:ns] if reps > 1 else hq0[:ns]
         rate, cids, dt = cpu_search_rate(O, host_vecs, og, sample_q, k, ef, norms, cores, native)
         same = float(np.mean(cids[:nq] == ids_np[: min(ns, nq)].astype(np.uint32))) if ns >= nq else float(np.mean(cids == ids_np[:ns].astype(np.uint32)))
+        rate1, _, _ = cpu_search_rate(O, host_vecs, og, hq0[:128], k, ef, norms, 1, native)      # one core, for the per-core figure
         cpu = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "sample": f"{ns} queries (the timed batches{', repeated' if reps > 1 else ''}), {dt:.1f} s",
-               "native_isa": native, "ids_identical_to_gpu": same}
+               "native_isa": native, "ids_identical_to_gpu": same, "single_thread_qps": rate1}
 
     if rank == 0:
         qps_units = world * nq * args.steps / (ms_total * 1e-3)
