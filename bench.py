@@ -184,6 +184,28 @@ def cpu_search_rate(O, host_vecs, og, host_q, k, ef, norms, threads, native):
     return len(host_q) / dt, ids, dt
 
 
+def run_cpu_baseline(O, host_vecs, og, hq0, gpu_ids_first_batch, nq, k, ef, cores, cpu_seconds):
+    """The `cpu_baseline` object: the oracle's hnsw_search on `cores` host threads over a sample of the timed batches sized for
+    about `cpu_seconds` (the batches are repeated if they are too few), plus the single-thread rate and the agreement with the
+    GPU's ids on the first timed batch."""
+    try:
+        O.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    norms = O.norms(host_vecs, nthreads=cores)
+    rate, _, _ = cpu_search_rate(O, host_vecs, og, hq0[:256], k, ef, norms, cores, native)
+    ns = int(max(256, rate * cpu_seconds))
+    reps = -(-ns // len(hq0))                              # the timed batches, repeated until the sample is ~cpu_seconds long
+    sample_q = np.concatenate([hq0] * reps)[:ns] if reps > 1 else hq0[:ns]
+    rate, cids, dt = cpu_search_rate(O, host_vecs, og, sample_q, k, ef, norms, cores, native)
+    m = min(ns, nq, len(gpu_ids_first_batch))
+    same = float(np.mean(cids[:m] == gpu_ids_first_batch[:m].astype(np.uint32)))
+    rate1, _, _ = cpu_search_rate(O, host_vecs, og, hq0[:128], k, ef, norms, 1, native)      # one core, for the per-core figure
+    return {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "sample": f"{ns} queries (the timed batches{', repeated' if reps > 1 else ''}), {dt:.1f} s",
+            "native_isa": native, "ids_identical_to_gpu": same, "single_thread_qps": rate1}
+
+
 def main():
     args = parse_args()
     import torch
@@ -472,23 +494,9 @@ def main():
     if rank == 0 and host_vecs is not None:
         import oracle as O
 
-        try:
-            O.build(native=True)
-            native = True
-        except Exception:
-            native = False
         og = export_graph_for_oracle(seg, O, n, m, m0)
-        norms = O.norms(host_vecs, nthreads=cores)
         hq0 = torch.cat(queries[args.warmup:]).cpu().numpy()   # the timed batches, in order
-        rate, _, _ = cpu_search_rate(O, host_vecs, og, hq0[:256], k, ef, norms, cores, native)
-        ns = int(max(256, rate * args.cpu_seconds))
-        reps = -(-ns // len(hq0))                              # the timed batches, repeated until the sample is ~cpu_seconds long
-        sample_q = np.concatenate([hq0] * reps)[:ns] if reps > 1 else hq0[:ns]
-        rate, cids, dt = cpu_search_rate(O, host_vecs, og, sample_q, k, ef, norms, cores, native)
-        same = float(np.mean(cids[:nq] == ids_np[: min(ns, nq)].astype(np.uint32))) if ns >= nq else float(np.mean(cids == ids_np[:ns].astype(np.uint32)))
-        rate1, _, _ = cpu_search_rate(O, host_vecs, og, hq0[:128], k, ef, norms, 1, native)      # one core, for the per-core figure
-        cpu = {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "sample": f"{ns} queries (the timed batches{', repeated' if reps > 1 else ''}), {dt:.1f} s",
-               "native_isa": native, "ids_identical_to_gpu": same, "single_thread_qps": rate1}
+        cpu = run_cpu_baseline(O, host_vecs, og, hq0, ids_np, nq, k, ef, cores, args.cpu_seconds)
 
     if rank == 0:
         qps_units = world * nq * args.steps / (ms_total * 1e-3)

@@ -144,3 +144,21 @@ def test_warp_chunked_assignment_covers_every_posting_once():
                             assert l == locate(pre, nt, i) and 0 <= i - pre[l] < counts[l]
                             seen[i] += 1
             assert (seen == 1).all()
+
+
+# ---- bench.py's CPU-side pieces (they run on the GPU box's host cores; exercised here on a small graph) -----------------------------
+def test_bench_cpu_baseline_block():
+    import bench
+    from conftest import make_queries, make_vectors
+
+    v = make_vectors(3000, 32, seed=50)
+    g = O.hnsw_build(v, M=8, M0=16, efC=40, max_batch=64, nthreads=4)
+    nq, k, ef = 64, 10, 32
+    hq0 = np.concatenate([make_queries(v, nq, seed=60 + i) for i in range(3)])        # three "timed batches"
+    gpu_ids, _, _, _ = O.hnsw_search(v, g, hq0[:nq], k, ef, nthreads=2)               # stands in for the GPU's first batch
+    line = bench.run_cpu_baseline(O, v, g, hq0, gpu_ids.astype(np.int32), nq, k, ef, cores=2, cpu_seconds=0.2)
+    assert line["kind"] == "port" and line["cores"] == 2 and line["unit"] == "queries/s"
+    assert line["value"] > 0 and line["single_thread_qps"] > 0 and line["ids_identical_to_gpu"] == 1.0
+    assert "repeated" in line["sample"]                                               # 192 queries do not last 0.2 s: the batches repeat
+    assert bench.effective_cores() >= 1
+    assert bench.recall_at_k(gpu_ids, gpu_ids) == 1.0
