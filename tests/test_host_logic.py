@@ -162,3 +162,22 @@ def test_bench_cpu_baseline_block():
     assert "repeated" in line["sample"]                                               # 192 queries do not last 0.2 s: the batches repeat
     assert bench.effective_cores() >= 1
     assert bench.recall_at_k(gpu_ids, gpu_ids) == 1.0
+
+
+def test_bench_generators_and_clock_sampler_degrade_gracefully():
+    import torch
+
+    import bench
+
+    dev = torch.device("cpu")
+    v = bench.gen_vectors(2000, 48, dev, seed=1, latent=8, noise=0.15)
+    assert v.shape == (2000, 48) and v.dtype == torch.float32
+    assert torch.allclose(v.norm(dim=1), torch.ones(2000), atol=1e-5)                  # L2-normalised
+    q = bench.gen_queries(v, 16, seed=2)
+    assert q.shape == (16, 48) and torch.allclose(q.norm(dim=1), torch.ones(16), atol=1e-5)
+    assert (q @ v.T).max(dim=1).values.min() > 0.9                                     # queries sit next to data points
+    clocks = bench.ClockSampler(0)                                                      # no NVML / no GPU here: must not raise
+    with clocks:
+        pass
+    s = clocks.summary()
+    assert isinstance(s, dict) and "reasons" in s
