@@ -181,3 +181,27 @@ def test_bench_generators_and_clock_sampler_degrade_gracefully():
         pass
     s = clocks.summary()
     assert isinstance(s, dict) and "reasons" in s
+
+
+def test_paragraph_store_round_trip_property():
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from nucliadb_b200 import paragraph_store as PS
+
+    paragraph = st.tuples(st.text(max_size=40), st.lists(st.text(max_size=12), max_size=4), st.one_of(st.none(), st.binary(min_size=1, max_size=300)),
+                          st.integers(0, 2 ** 32 - 1), st.integers(0, 2 ** 32 - 1))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(paragraph, max_size=6), st.integers(0, 2 ** 64 - 1))
+    def check(paragraphs, u):
+        blob = b"".join(PS.encode_paragraph(*p) for p in paragraphs)
+        pos, back = 0, []
+        for _ in paragraphs:
+            p, pos = PS.decode_paragraph(blob, pos)
+            back.append(p)
+        assert pos == len(blob) and back == [(k, list(l), m, f, n) for k, l, m, f, n in paragraphs]
+        enc = PS.encode_varint(u)
+        assert PS.decode_varint(enc, 0) == (u, len(enc)) and len(enc) in (1, 3, 5, 9)
+
+    check()
