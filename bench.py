@@ -220,11 +220,16 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if multi:
-        try:     # the exchange kernel of batch i has to slip in between the CTAs of the search of batch i + 1
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.is_high_priority_stream = True
+        opts = None
+        if args.pipeline:   # the exchange kernel of batch i has to slip in between the CTAs of the search of batch i + 1
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.is_high_priority_stream = True
+            except Exception:
+                opts = None
+        if opts is not None:
             dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-        except Exception:
+        else:
             dist.init_process_group("nccl", device_id=dev)
 
     from nucliadb_b200 import _lib
