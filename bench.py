@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--noise", type=float, default=0.15)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="lib", choices=["lib", "torch"],
+                    help="N>1: 'lib' = nidx_vec_search_sharded (search -> ncclAllGather -> Fssc merge inside the library, one stream, no host code "
+                         "in between); 'torch' = round 1's torch.distributed all_gather + nidx_merge_topk")
     ap.add_argument("--pipeline", action="store_true",
                     help="N>1: two batches in flight (exchange of batch i under the search of batch i+1) instead of search -> exchange -> merge back to "
                          "back; measured 1.5 %% SLOWER at N=2 (profiles/r01c_bench_2M_n2_pipelined.json): the in-line exchange costs 0.02 ms of a 1.63 ms step")
@@ -306,11 +309,20 @@ def main():
         print(json.dumps(line))
         return 0
 
-    sharded = ShardedSearcher(seg, nq, k, local_rank) if multi else None
-
     pipelined = multi and args.pipeline
+    use_lib = multi and args.exchange == "lib" and not pipelined
+    sharded = ShardedSearcher(seg, nq, k, local_rank) if multi and not use_lib else None
+    comm = sh_out = None
+    if use_lib:   # the library's own NCCL communicator (the id travels over the torch group, the data path does not touch torch)
+        from nucliadb_b200.dist import ShardComm
+
+        comm = ShardComm(rank, world, local_rank)
+        sh_out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+                  torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq,), dtype=torch.int32, device=dev))
 
     def step(i):
+        if use_lib:  # local search -> ncclAllGather of the partials over NVLink -> Fssc merge (segments of ONE index), all inside the C ABI call
+            return comm.search_vectors(seg, queries[i], k, ef=ef, dedup=True, out=sh_out)
         if multi:  # local search -> ONE all_gather of the [2, nq, k] partials over NVLink -> in-place merge kernel
             return sharded.search(queries[i], ef)
         return seg.search(queries[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=out)
@@ -327,29 +339,44 @@ def main():
         sharded.collect()
 
     # ---- warm-up + timed region: inputs resident in HBM (value) --------------------------------------
+    # Everything with a host-side cost that differs between ranks (NVML initialisation: 8 processes contend for it on an
+    # 8-GPU node, event creation, the sampler thread) happens BEFORE the warm-up; the barrier + synchronize sit immediately
+    # before the first event, so no rank's clock runs while it waits for a slower rank's set-up.  (Round 1's N = 8 point
+    # had the NVML init between the barrier and the first event: 6.4 ms/step of skew against 1.8 ms/step of work.)
+    clocks = ClockSampler(local_rank)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]   # step i = step_ev[i] .. step_ev[i + 1]
     run_steps(0, args.warmup)
     torch.cuda.synchronize()
-    if multi:
-        dist.barrier()
     launches0 = L.nidx_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local_rank)
     with clocks:
+        if multi:
+            dist.barrier()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()  # `ncu --profile-from-start off` captures exactly the timed region
-        ev0.record()
-        run_steps(args.warmup, n_batches)
-        ev1.record()
+        step_ev[0].record()
+        if pipelined:
+            run_steps(args.warmup, n_batches)
+        else:
+            for i in range(args.warmup, n_batches):
+                step(i)
+                step_ev[i - args.warmup + 1].record()
+        step_ev[-1].record()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = step_ev[0].elapsed_time(step_ev[-1])
+    per_step = None if pipelined else [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
     launches = L.nidx_launch_count() - launches0
     if multi:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+        if per_step is not None:   # per-step spread: the slowest rank's time of every step
+            ps = torch.tensor(per_step, device=dev)
+            dist.all_reduce(ps, op=dist.ReduceOp.MAX)
+            per_step = [float(x) for x in ps.tolist()]
         dist.barrier()
     ms_step = ms_total / args.steps
+    step_ms = None if per_step is None else {"min": float(np.min(per_step)), "median": float(np.median(per_step)), "max": float(np.max(per_step))}
     inline_ms = None
     if pipelined:   # context: the same steps with search -> exchange -> merge back to back (what the pipelining removes)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -416,6 +443,10 @@ def main():
     e2e_steps = []
     dq = torch.empty((nq, d), dtype=torch.float32, device=dev)
     host_out = (torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory())
+    e2e_host_out = (np.empty((nq, k), dtype=np.uint32), np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int32), np.empty(nq, dtype=np.int32))
+    if use_lib:
+        for i in range(args.warmup):
+            comm.search_vectors(seg, hq_np[i], k, ef=ef, dedup=True, out=e2e_host_out)
     if multi:
         dist.barrier()
     def to_host(r):
@@ -436,7 +467,9 @@ def main():
         else:
             for i in range(args.warmup, n_batches):
                 t1 = time.perf_counter()
-                if multi:  # pinned host queries -> device, sharded search + exchange + merge, merged result -> pinned host
+                if use_lib:  # host queries in, merged host results out: H2D, search, exchange, merge and D2H inside ONE C ABI call
+                    comm.search_vectors(seg, hq_np[i], k, ef=ef, dedup=True, out=e2e_host_out)
+                elif multi:  # pinned host queries -> device, sharded search + exchange + merge, merged result -> pinned host
                     dq.copy_(hq[i], non_blocking=True)
                     to_host(sharded.search(dq, ef))
                     torch.cuda.synchronize()
@@ -507,8 +540,8 @@ def main():
         qps_units = world * nq * args.steps / (ms_total * 1e-3)
         line = {
             "metric": "k-NN QPS @ recall@10", "value": qps_units, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "segments": world, "vectors_per_segment": n, "exchange": ("pipelined, 2 batches in flight" if pipelined else "in line") if multi else None,
+            "ms_per_step": ms_step, "step_ms": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "segments": world, "vectors_per_segment": n, "exchange": ("pipelined, 2 batches in flight (torch)" if pipelined else ("in line, nidx_vec_search_sharded (ncclAllGather + Fssc merge in the library)" if use_lib else "in line, torch all_gather + nidx_merge_topk")) if multi else None,
                        "M": m, "M0": m0, "efC": args.efc, "l2": f"inputs larger than L2 ({n * d * 4 / 1e9:.1f} GB of vectors per GPU, fresh queries every step)",
                        "unit_note": "one unit = one query searched on one segment; merged_qps = user-visible queries/s over all segments",
                        "data_gen": f"latent={args.latent} noise={args.noise} normalised; queries = data point + 0.05 * unit noise"},
@@ -522,12 +555,14 @@ def main():
                          "traffic_source": "profiles/ncu_traffic.json" if traffic else None, "kernel": "hnsw_search_kernel", "kernel_ms": float(np.mean(kernel_ms)), "alg_bytes_per_launch": float(np.mean(alg_bytes)),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4, **e2e_mode},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * (12 if use_lib else 8) + nq * 4, **e2e_mode},
             "gpu_launches": int(launches),
             "visited_overflows": int(overflow),
             "clocks": clocks.summary(),
         }
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if multi:
         dist.destroy_process_group()
     return 0

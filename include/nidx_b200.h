@@ -217,6 +217,45 @@ int nidx_txt_search(nidx_txt_segment* seg, const uint32_t* query_terms, const ui
                     const nidx_txt_search_params* p, uint32_t* out_docs, float* out_scores, int32_t* out_counts, uint64_t* out_total,
                     void* stream);
 
+/* Device time (CUDA events on the caller's stream) of bm25_kernel in the last nidx_txt_search on this segment (bench roofline);
+ * not meaningful under concurrent searches. */
+int nidx_txt_last_kernel_ms(nidx_txt_segment* seg, float* ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Segments sharded over the GPUs of one node: one process (or thread) per GPU, one segment each
+ * (reference: the searcher's scatter-gather, nidx/src/searcher/grpc.rs:253-431, merged by
+ *  shard_merge.rs:332-348 / 177-231; inside one index the cross-segment collection Fssc, nidx_vector/src/searcher.rs:150-199)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nidx_shard_comm nidx_shard_comm;
+
+/* ncclGetUniqueId: rank 0 creates the 128-byte id and hands it to the other ranks by whatever channel the host has
+ * (the reference's searchers already know each other through their gRPC addresses). */
+int nidx_shard_unique_id(uint8_t out_id[128]);
+/* ncclCommInitRank on `device`; collective: every rank of `world` must call it with the same id.  NCCL is bound at run time
+ * (libnccl.so.2); without it these entry points fail with NIDX_ESTATE and everything else keeps working. */
+int nidx_shard_init(const uint8_t unique_id[128], int32_t rank, int32_t world, int32_t device, nidx_shard_comm** out);
+void nidx_shard_destroy(nidx_shard_comm* comm);
+
+/* Paragraph keys for the cross-segment de-duplication: keys[p] identifies paragraph p's id across segments (the reference keys
+ * Fssc by the paragraph id string, searcher.rs:62-90: pass a 64-bit hash of it).  NULL = (rank, paragraph address). Host pointer. */
+int nidx_vec_set_paragraph_keys(nidx_vec_segment* seg, const uint64_t* keys);
+
+/* OpenSegment::search on this rank's segment + exchange + merge, identical results on every rank.  Collective: every rank calls
+ * it with the same queries, nq, k and dedup, in the same order (one call at a time per communicator).
+ *   dedup = 0: the parts are shards -- merge_vector_responses (kmerge by score, shard_merge.rs:332-348);
+ *   dedup = 1: the parts are segments of ONE index -- Fssc (searcher.rs:150-199): one entry per paragraph key, and with
+ *              p->with_duplicates == 0 byte-identical vectors are suppressed across segments (by a 64-bit hash of the bytes).
+ * out_ids are vector addresses local to the part in out_part[nq][k] (-1 = none); out_counts[nq] may be NULL.
+ * `mem` applies to queries and outputs; device calls are asynchronous on `stream`. */
+int nidx_vec_search_sharded(nidx_shard_comm* comm, nidx_vec_segment* seg, const float* queries, int32_t nq, int32_t ldq, int mem,
+                            const nidx_vec_search_params* p, int32_t dedup, uint32_t* out_ids, float* out_scores, int32_t* out_part, int32_t* out_counts,
+                            void* stream);
+/* BM25 over a document-partitioned index (every part scores with the statistics of the whole index, nidx_txt_set_stats):
+ * merge_document_responses' order (bm25 desc, part asc, doc asc; shard_merge.rs:227-231); out_total = Count over all parts. */
+int nidx_txt_search_sharded(nidx_shard_comm* comm, nidx_txt_segment* seg, const uint32_t* query_terms, const uint32_t* query_off, int32_t nq, int mem,
+                            const nidx_txt_search_params* p, uint32_t* out_docs, float* out_scores, int32_t* out_part, int32_t* out_counts, uint64_t* out_total,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,8 @@ SYMBOLS = [
     "nidx_use_hnsw", "nidx_hnsw_levels", "nidx_vec_build_hnsw", "nidx_vec_extend_hnsw", "nidx_vec_graph_dims", "nidx_vec_set_graph", "nidx_vec_get_graph", "nidx_vec_set_alive",
     "nidx_vec_search", "nidx_merge_topk", "nidx_vec_counters", "nidx_vec_last_kernel_ms",
     "nidx_vec_rabitq_encode", "nidx_vec_rabitq_codes", "nidx_vec_rabitq_estimate",
-    "nidx_txt_create", "nidx_txt_set_stats", "nidx_txt_set_alive", "nidx_txt_close", "nidx_txt_search",
+    "nidx_txt_create", "nidx_txt_set_stats", "nidx_txt_set_alive", "nidx_txt_close", "nidx_txt_search", "nidx_txt_last_kernel_ms",
+    "nidx_shard_unique_id", "nidx_shard_init", "nidx_shard_destroy", "nidx_vec_set_paragraph_keys", "nidx_vec_search_sharded", "nidx_txt_search_sharded",
 ]
 
 
@@ -69,6 +70,7 @@ def load():
     L.nidx_vec_device_vectors.restype = C.c_void_p
     L.nidx_vec_close.restype = None
     L.nidx_txt_close.restype = None
+    L.nidx_shard_destroy.restype = None
     _lib = L
     return L
 

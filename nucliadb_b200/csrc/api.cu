@@ -15,7 +15,6 @@
 
 #include "../../include/nidx_b200.h"
 #include "bm25.cuh"
-#include "bm25_w.cuh"
 #include "common.cuh"
 #include "hnsw_build.cuh"
 #include "hnsw_search.cuh"
@@ -23,6 +22,7 @@
 #include "scan.cu"
 #include "scan_tc.cuh"
 #include "segment_io.hpp"
+#include "shard.cuh"
 #include "topk.cuh"
 
 using namespace nidx;
@@ -124,6 +124,7 @@ struct nidx_vec_segment {
     uint32_t* d_par_first = nullptr;
     uint32_t n_par = 0;
     uint64_t* d_alive = nullptr;
+    uint64_t* d_par_keys = nullptr;   // [n_par] caller-supplied paragraph keys for the cross-segment de-duplication (shard.cuh)
     // graph
     bool has_graph = false;
     std::vector<uint8_t> h_level;
@@ -328,7 +329,7 @@ void nidx_vec_close(nidx_vec_segment* s) {
     cudaDeviceSynchronize();
     free_graph(s);
     cudaFree(s->d_vecs); cudaFree(s->d_norms); cudaFree(s->d_par_of); cudaFree(s->d_par_first); cudaFree(s->d_alive);
-    cudaFree(s->d_counters); cudaFree(s->d_work_counter); cudaFree(s->d_quant);
+    cudaFree(s->d_counters); cudaFree(s->d_work_counter); cudaFree(s->d_quant); cudaFree(s->d_par_keys);
     if (s->ev_k0) cudaEventDestroy(s->ev_k0);
     if (s->ev_k1) cudaEventDestroy(s->ev_k1);
     delete s;
@@ -574,18 +575,22 @@ static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list
     return 0;
 }
 
-int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p, uint32_t* out_ids,
-                    float* out_scores, int32_t* out_counts, void* stream_) {
+}  // extern "C"
+
+// The body of nidx_vec_search.  qhost: the queries (and filter bits) are host pointers; ohost: the outputs are host pointers
+// (copied back and the stream synchronised before returning).  The sharded entry point (shard.cuh) passes host queries with
+// device outputs: the partial results go straight into the exchange buffer.
+static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq, int32_t ldq, bool qhost, bool ohost, const nidx_vec_search_params* p,
+                           uint32_t* out_ids, float* out_scores, int32_t* out_counts, cudaStream_t stream) {
     if (!s || !p || (!queries && nq > 0) || !out_ids || !out_scores) return fail(NIDX_EINVAL, "null argument");
     if (nq <= 0) return 0;
     if (ldq < s->d) return fail(NIDX_EINVAL, "query dimension %d != index dimension %d (VectorErr::InconsistentDimensions)", ldq, s->d);
     int k = p->k;
     if (k <= 0) return fail(NIDX_EINVAL, "k must be positive");
     CU(cudaSetDevice(s->cfg.device));
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     WsGuard g(s->pool, stream);
     Workspace& w = *g.w;
-    bool host = mem == NIDX_MEM_HOST;
+    bool host = qhost;
     VecDev V = s->vdev();
 
     // queries -> [nq][ld] zero padded on device, norms
@@ -649,12 +654,12 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
 
     // outputs
     uint32_t* d_ids = out_ids; float* d_sc = out_scores; int* d_cnt = out_counts;
-    if (host || !out_counts) {
+    if (ohost || !out_counts) {
         ENSURE(w.out_ids, (size_t)nq * k * 4);
         ENSURE(w.out_scores, (size_t)nq * k * 4);
         ENSURE(w.out_counts, (size_t)nq * 4);
-        if (host) { d_ids = w.out_ids.as<uint32_t>(); d_sc = w.out_scores.as<float>(); }
-        if (host || !out_counts) d_cnt = w.out_counts.as<int>();
+        if (ohost) { d_ids = w.out_ids.as<uint32_t>(); d_sc = w.out_scores.as<float>(); }
+        if (ohost || !out_counts) d_cnt = w.out_counts.as<int>();
     }
 
     if (method == NIDX_METHOD_BRUTE_RABITQ && s->n != 0) {
@@ -770,13 +775,21 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
         CU(cudaGetLastError());
     }
 
-    if (host) {
+    if (ohost) {
         CU(cudaMemcpyAsync(out_ids, d_ids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
         CU(cudaMemcpyAsync(out_scores, d_sc, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
         if (out_counts) CU(cudaMemcpyAsync(out_counts, d_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
     }
     return 0;
+}
+
+extern "C" {
+
+int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p, uint32_t* out_ids,
+                    float* out_scores, int32_t* out_counts, void* stream_) {
+    bool host = mem == NIDX_MEM_HOST;
+    return vec_search_impl(s, queries, nq, ldq, host, host, p, out_ids, out_scores, out_counts, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int64_t part_stride, int32_t nq, int32_t k,
@@ -1169,19 +1182,18 @@ struct nidx_txt_segment {
     uint32_t n_docs = 0, n_terms = 0;
     uint64_t n_post = 0;
     uint64_t* d_term_off = nullptr;
-    uint32_t* d_doc = nullptr;
-    uint32_t* d_tfn = nullptr;        // tf << 8 | fieldnorm id
+    uint2* d_post = nullptr;          // (doc, tf << 8 | fieldnorm id)
     uint32_t* d_skip_row = nullptr;   // [n_terms]
-    uint32_t* d_skip = nullptr;       // [rows][n_tiles + 1]
-    uint32_t n_tiles = 0;
-    unsigned char* d_fieldnorm = nullptr;
+    uint32_t* d_skip = nullptr;       // [rows][n_fine + 1]
+    uint32_t n_fine = 0;
     uint64_t* d_alive = nullptr;
     float* d_weight = nullptr;   // [n_terms]
     float* d_norm_cache = nullptr;  // [256]
+    unsigned int* d_error = nullptr;
     std::vector<uint64_t> own_df;
     uint64_t own_tokens = 0;
     float max_weight = 0.0f;
-    std::vector<float> h_weight;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around bm25_kernel of the last search (bench roofline)
     WorkspacePool pool;
 };
 
@@ -1197,13 +1209,16 @@ static int txt_upload_stats(nidx_txt_segment* t, uint64_t total_docs, uint64_t t
     float avg = (float)total_tokens / (float)total_docs;
     float cache[256];
     for (int i = 0; i < 256; ++i) cache[i] = K1 * (1.0f - B + B * (float)fieldnorm_id_to_value(i) / avg);
-    t->h_weight.resize(t->n_terms);
+    std::vector<float> weight(t->n_terms);
+    float wmax = 0.0f;
     for (uint32_t i = 0; i < t->n_terms; ++i) {
         float x = ((float)(total_docs - df[i]) + 0.5f) / ((float)df[i] + 0.5f);
-        t->h_weight[i] = logf(1.0f + x) * (1.0f + K1);
+        weight[i] = logf(1.0f + x) * (1.0f + K1);
+        wmax = std::max(wmax, weight[i]);
     }
+    t->max_weight = wmax;
     CU(cudaMemcpy(t->d_norm_cache, cache, sizeof(cache), cudaMemcpyHostToDevice));
-    if (t->n_terms) CU(cudaMemcpy(t->d_weight, t->h_weight.data(), (size_t)t->n_terms * 4, cudaMemcpyHostToDevice));
+    if (t->n_terms) CU(cudaMemcpy(t->d_weight, weight.data(), (size_t)t->n_terms * 4, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -1219,41 +1234,47 @@ int nidx_txt_create(int32_t device, uint32_t n_docs, uint32_t n_terms, const uin
     cudaGetDeviceProperties(&prop, device);
     t->sm_count = prop.multiProcessorCount;
     r = [&]() -> int {
-        t->n_tiles = (n_docs + BM_TILE - 1) / BM_TILE;
+        t->n_fine = (n_docs + BM_FINE - 1) / BM_FINE;
         CU(cudaMalloc(&t->d_term_off, ((size_t)n_terms + 1) * 8));
-        CU(cudaMalloc(&t->d_doc, std::max<uint64_t>(t->n_post, 1) * 4));
-        CU(cudaMalloc(&t->d_tfn, std::max<uint64_t>(t->n_post, 1) * 4));
-        CU(cudaMalloc(&t->d_fieldnorm, std::max<uint32_t>(n_docs, 1)));
+        CU(cudaMalloc(&t->d_post, std::max<uint64_t>(t->n_post, 1) * 8));
         CU(cudaMalloc(&t->d_weight, std::max<uint32_t>(n_terms, 1) * 4));
         CU(cudaMalloc(&t->d_norm_cache, 1024));
         CU(cudaMalloc(&t->d_skip_row, std::max<uint32_t>(n_terms, 1) * 4));
+        CU(cudaMalloc(&t->d_error, 4));
+        CU(cudaMemset(t->d_error, 0, 4));
+        CU(cudaEventCreate(&t->ev_k0));
+        CU(cudaEventCreate(&t->ev_k1));
         CU(cudaMemcpy(t->d_term_off, term_off, ((size_t)n_terms + 1) * 8, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(t->d_fieldnorm, fieldnorm_id, n_docs, cudaMemcpyHostToDevice));
         if (t->n_post) {
-            CU(cudaMemcpy(t->d_doc, post_doc, t->n_post * 4, cudaMemcpyHostToDevice));
-            uint32_t* d_tf = nullptr;   // staged only to be packed with the fieldnorm code
+            // staged only to be packed into the 8-byte posting records
+            uint32_t *d_doc = nullptr, *d_tf = nullptr;
+            unsigned char* d_fn = nullptr;
+            CU(cudaMalloc(&d_doc, t->n_post * 4));
+            CU(cudaMalloc(&d_fn, std::max<uint32_t>(n_docs, 1)));
+            CU(cudaMemcpy(d_doc, post_doc, t->n_post * 4, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d_fn, fieldnorm_id, n_docs, cudaMemcpyHostToDevice));
             if (post_tf) {
                 CU(cudaMalloc(&d_tf, t->n_post * 4));
                 CU(cudaMemcpy(d_tf, post_tf, t->n_post * 4, cudaMemcpyHostToDevice));
             }
-            bm25_pack_tfn_kernel<<<t->sm_count * 8, 256>>>(t->d_doc, d_tf, t->d_fieldnorm, t->n_post, t->d_tfn);
+            bm25_pack_kernel<<<t->sm_count * 8, 256>>>(d_doc, d_tf, d_fn, t->n_post, t->d_post);
             LAUNCHED();
             CU(cudaGetLastError());
             CU(cudaDeviceSynchronize());
-            cudaFree(d_tf);
+            cudaFree(d_doc); cudaFree(d_tf); cudaFree(d_fn);
         }
         // skip rows for the terms with enough postings
         std::vector<uint32_t> skip_row(n_terms, NIDX_NIL), row_term;
         for (uint32_t i = 0; i < n_terms; ++i)
             if (term_off[i + 1] - term_off[i] >= (uint64_t)BM_SKIP_DF) { skip_row[i] = (uint32_t)row_term.size(); row_term.push_back(i); }
         if (n_terms) CU(cudaMemcpy(t->d_skip_row, skip_row.data(), (size_t)n_terms * 4, cudaMemcpyHostToDevice));
-        size_t skip_words = std::max<size_t>(row_term.size(), 1) * (t->n_tiles + 1);
+        size_t skip_words = std::max<size_t>(row_term.size(), 1) * ((size_t)t->n_fine + 1);
         CU(cudaMalloc(&t->d_skip, skip_words * 4));
         if (!row_term.empty()) {
             uint32_t* d_row_term = nullptr;
             CU(cudaMalloc(&d_row_term, row_term.size() * 4));
             CU(cudaMemcpy(d_row_term, row_term.data(), row_term.size() * 4, cudaMemcpyHostToDevice));
-            bm25_build_skip_kernel<<<t->sm_count * 8, 256>>>(t->d_term_off, t->d_doc, d_row_term, (uint32_t)row_term.size(), t->n_tiles, t->d_skip);
+            bm25_build_skip_kernel<<<t->sm_count * 8, 256>>>(t->d_term_off, t->d_post, d_row_term, (uint32_t)row_term.size(), t->n_fine, t->d_skip);
             LAUNCHED();
             CU(cudaGetLastError());
             CU(cudaDeviceSynchronize());
@@ -1292,32 +1313,45 @@ void nidx_txt_close(nidx_txt_segment* t) {
     if (!t) return;
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
-    cudaFree(t->d_term_off); cudaFree(t->d_doc); cudaFree(t->d_tfn); cudaFree(t->d_skip_row); cudaFree(t->d_skip); cudaFree(t->d_fieldnorm); cudaFree(t->d_alive); cudaFree(t->d_weight);
-    cudaFree(t->d_norm_cache);
+    cudaFree(t->d_term_off); cudaFree(t->d_post); cudaFree(t->d_skip_row); cudaFree(t->d_skip); cudaFree(t->d_alive); cudaFree(t->d_weight);
+    cudaFree(t->d_norm_cache); cudaFree(t->d_error);
+    if (t->ev_k0) cudaEventDestroy(t->ev_k0);
+    if (t->ev_k1) cudaEventDestroy(t->ev_k1);
     delete t;
 }
 
-int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint32_t* query_off, int32_t nq, int mem, const nidx_txt_search_params* p,
-                    uint32_t* out_docs, float* out_scores, int32_t* out_counts, uint64_t* out_total, void* stream_) {
+int nidx_txt_last_kernel_ms(nidx_txt_segment* t, float* ms) {
+    if (!t || !ms) return fail(NIDX_EINVAL, "null argument");
+    CU(cudaSetDevice(t->device));
+    CU(cudaEventSynchronize(t->ev_k1));
+    CU(cudaEventElapsedTime(ms, t->ev_k0, t->ev_k1));
+    return 0;
+}
+
+}  // extern "C"
+
+typedef void (*bm_kernel_t)(TxtDev, Bm25Args);
+
+// The body of nidx_txt_search.  qhost / ohost as in vec_search_impl.
+static int txt_search_impl(nidx_txt_segment* t, const uint32_t* query_terms, const uint32_t* query_off, int32_t nq, bool qhost, bool ohost,
+                           const nidx_txt_search_params* p, uint32_t* out_docs, float* out_scores, int32_t* out_counts, uint64_t* out_total, cudaStream_t stream) {
     if (!t || !p || !query_off || !out_docs || !out_scores || !out_counts) return fail(NIDX_EINVAL, "null argument");
     if (nq <= 0) return 0;
     int k = p->k;
     if (k <= 0 || k > 1024) return fail(NIDX_EINVAL, "k must be in 1..1024");
     CU(cudaSetDevice(t->device));
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    bool host = mem == NIDX_MEM_HOST;
     WsGuard g(t->pool, stream);
     Workspace& w = *g.w;
     // query offsets are needed on the host to size things
     std::vector<uint32_t> h_off(nq + 1);
-    if (host) memcpy(h_off.data(), query_off, ((size_t)nq + 1) * 4);
+    if (qhost) memcpy(h_off.data(), query_off, ((size_t)nq + 1) * 4);
     else { CU(cudaMemcpyAsync(h_off.data(), query_off, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, stream)); CU(cudaStreamSynchronize(stream)); }
     uint32_t n_qt = h_off[nq];
     int max_terms = 0;
     for (int i = 0; i < nq; ++i) max_terms = std::max<int>(max_terms, h_off[i + 1] - h_off[i]);
     if (max_terms > BM_MAX_TERMS) return fail(NIDX_EINVAL, "queries with more than %d terms are not supported", BM_MAX_TERMS);
     const uint32_t *d_qt = query_terms, *d_qo = query_off;
-    if (host) {
+    if (qhost) {
         ENSURE(w.queries, ((size_t)n_qt + nq + 1) * 4 + 16);
         uint32_t* base = w.queries.as<uint32_t>();
         CU(cudaMemcpyAsync(base, query_off, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, stream));
@@ -1325,19 +1359,22 @@ int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint
         d_qo = base; d_qt = base + nq + 1;
     }
     // fixed-point scale: the largest possible sum is max_terms * max term weight (tf factor < 1)
-    float wmax = 0.0f;
-    for (float x : t->h_weight) wmax = std::max(wmax, x);
-    float bound = std::max(1.0f, wmax * (float)std::max(max_terms, 1));
+    float bound = std::max(1.0f, t->max_weight * (float)std::max(max_terms, 1));
     int shift = 24;
     while (shift > 4 && bound * (float)(1u << shift) >= 4.0e9f) --shift;
 
-    int cap = next_pow2(std::max(2 * k, k + BM_THREADS * BM_ROUND));
-    size_t smem = bm_smem_bytes(cap, p->mode == NIDX_BM25_AND);
+    bool conj = p->mode == NIDX_BM25_AND;
+    int cap = topk_cap(k, BM_THREADS);
+    // accumulator table: 8192 slots (two CTAs per SM); NIDX_B200_BM25_BITS overrides (13..15) for experiments
+    int hash_bits = 13;
+    if (const char* e = getenv("NIDX_B200_BM25_BITS")) { int b = atoi(e); if (b >= 13 && b <= 15) hash_bits = b; }
+    size_t smem = bm_smem_bytes(cap, hash_bits, conj);
+    if (smem > 220 * 1024) return fail(NIDX_EINVAL, "BM25 needs %zu bytes of shared memory (k=%d): too large", smem, k);
     ENSURE(w.partial, (size_t)nq * k * 8);
     ENSURE(w.misc, (size_t)nq * 8);
     uint32_t* d_docs = out_docs; float* d_sc = out_scores; int* d_cnt = out_counts;
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(out_total);
-    if (host) {
+    if (ohost) {
         ENSURE(w.out_ids, (size_t)nq * k * 4);
         ENSURE(w.out_scores, (size_t)nq * k * 4);
         ENSURE(w.out_counts, (size_t)nq * 4);
@@ -1345,43 +1382,209 @@ int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint
         d_total = w.misc.as<unsigned long long>();
     }
     TxtDev T;
-    T.n_docs = t->n_docs; T.n_terms = t->n_terms; T.n_tiles = t->n_tiles; T.term_off = t->d_term_off; T.post_doc = t->d_doc; T.post_tfn = t->d_tfn;
+    T.n_docs = t->n_docs; T.n_terms = t->n_terms; T.n_fine = t->n_fine; T.term_off = t->d_term_off; T.post = t->d_post;
     T.skip_row = t->d_skip_row; T.skip = t->d_skip; T.alive = t->d_alive;
     Bm25Args a;
-    a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.mode = p->mode; a.use_tf = p->use_tf; a.k = k; a.cap = cap;
+    a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.k = k; a.cap = cap; a.hash_bits = hash_bits;
     a.term_weight = t->d_weight; a.norm_cache = t->d_norm_cache; a.shift = shift;
-    a.after_mode = p->after_mode; a.after_score = p->after_score; a.after_docaddr = p->after_docaddr; a.docaddr_base = p->docaddr_base; a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total;
-    // NIDX_B200_BM25=tm selects the term-major variant (warp per term slice, no scan / search, two barriers per tile).
-    // Measured SLOWER than the flattened kernel on the 5M-doc / 50-term workload (97k vs 169k QPS: 12-posting slices
-    // leave 60 % of the lanes idle and serialise a warp's terms), so it stays an experiment.
-    const char* bm_env = getenv("NIDX_B200_BM25");
-    // NIDX_B200_BM25=w128 | w256: the warp-chunked variant (bm25_w.cuh: one term search per lane and round, ratio table for tf == 1),
-    // bit-identical arithmetic; not measured yet, so not the default.
-    if (bm_env && (!strcmp(bm_env, "w128") || !strcmp(bm_env, "w256"))) {
-        size_t smem_w = bw_smem_bytes(cap, p->mode == NIDX_BM25_AND);
-        if (!strcmp(bm_env, "w128")) {
-            CU(cudaFuncSetAttribute(bm25_w_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-            bm25_w_kernel<128, 4><<<nq, 128, smem_w, stream>>>(T, a);
-        } else {
-            CU(cudaFuncSetAttribute(bm25_w_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-            bm25_w_kernel<256, 2><<<nq, 256, smem_w, stream>>>(T, a);
-        }
-    } else if (max_terms <= BM_TM_TERMS && bm_env && !strcmp(bm_env, "tm")) {
-        size_t smem_tm = bm_tm_smem_bytes(cap, p->mode == NIDX_BM25_AND);
-        CU(cudaFuncSetAttribute(bm25_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tm));
-        bm25_tm_kernel<<<nq, BM_THREADS, smem_tm, stream>>>(T, a);
-    } else {
-        CU(cudaFuncSetAttribute(bm25_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bm25_kernel<<<nq, BM_THREADS, smem, stream>>>(T, a);
-    }
+    a.after_mode = p->after_mode; a.after_score = p->after_score; a.after_docaddr = p->after_docaddr; a.docaddr_base = p->docaddr_base;
+    a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total; a.error_flag = t->d_error;
+    bm_kernel_t kern = conj ? (p->use_tf ? bm25_kernel<true, true> : bm25_kernel<true, false>) : (p->use_tf ? bm25_kernel<false, true> : bm25_kernel<false, false>);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaEventRecord(t->ev_k0, stream));
+    kern<<<nq, BM_THREADS, smem, stream>>>(T, a);
+    CU(cudaEventRecord(t->ev_k1, stream));
     LAUNCHED();
     bm25_finish_kernel<<<nq, 128, 0, stream>>>(w.partial.as<uint64_t>(), nq, k, p->min_score, d_docs, d_sc, d_cnt);
     LAUNCHED();
     CU(cudaGetLastError());
-    if (host) {
+    if (ohost) {
         CU(cudaMemcpyAsync(out_docs, d_docs, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
         CU(cudaMemcpyAsync(out_scores, d_sc, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
         CU(cudaMemcpyAsync(out_counts, d_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+        if (out_total) CU(cudaMemcpyAsync(out_total, d_total, (size_t)nq * 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        unsigned int err = 0;   // an accumulator table that filled up would mean incomplete sums: report, never return them silently
+        CU(cudaMemcpy(&err, t->d_error, 4, cudaMemcpyDeviceToHost));
+        if (err) { cudaMemset(t->d_error, 0, 4); return fail(NIDX_EOVERFLOW, "BM25 accumulator table overflow"); }
+    }
+    return 0;
+}
+
+extern "C" {
+
+int nidx_txt_search(nidx_txt_segment* t, const uint32_t* query_terms, const uint32_t* query_off, int32_t nq, int mem, const nidx_txt_search_params* p,
+                    uint32_t* out_docs, float* out_scores, int32_t* out_counts, uint64_t* out_total, void* stream_) {
+    bool host = mem == NIDX_MEM_HOST;
+    return txt_search_impl(t, query_terms, query_off, nq, host, host, p, out_docs, out_scores, out_counts, out_total, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// ---- sharded search (shard.cuh) -------------------------------------------------------------------
+struct nidx_shard_comm {
+    int rank = 0, world = 1, device = 0;
+    nccl_comm_t comm = nullptr;
+    std::mutex mu;          // collectives on one communicator must be issued in the same order by every rank: one call at a time
+    DevBuf local, gathered, total;
+};
+
+#define NC(expr)                                                                                                   \
+    do {                                                                                                           \
+        int e__ = (expr);                                                                                          \
+        if (e__ != NCCL_SUCCESS) return fail(NIDX_ECUDA, "%s failed: %s", #expr, nccl_api().GetErrorString(e__)); \
+    } while (0)
+
+int nidx_shard_unique_id(uint8_t out[128]) {
+    if (!out) return fail(NIDX_EINVAL, "null argument");
+    NcclApi& N = nccl_api();
+    if (!N.ok) return fail(NIDX_ESTATE, "NCCL (libnccl.so.2) is not available in this process");
+    nccl_unique_id id;
+    NC(N.GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+    return 0;
+}
+
+int nidx_shard_init(const uint8_t unique_id[128], int32_t rank, int32_t world, int32_t device, nidx_shard_comm** out) {
+    if (!unique_id || !out || world <= 0 || rank < 0 || rank >= world) return fail(NIDX_EINVAL, "bad argument");
+    int r = check_device(device);
+    if (r) return r;
+    NcclApi& N = nccl_api();
+    if (!N.ok) return fail(NIDX_ESTATE, "NCCL (libnccl.so.2) is not available in this process");
+    nidx_shard_comm* c = new nidx_shard_comm();
+    c->rank = rank; c->world = world; c->device = device;
+    nccl_unique_id id;
+    memcpy(id.internal, unique_id, 128);
+    int e = N.CommInitRank(&c->comm, world, id, rank);
+    if (e != NCCL_SUCCESS) { delete c; return fail(NIDX_ECUDA, "ncclCommInitRank failed: %s", N.GetErrorString(e)); }
+    *out = c;
+    return 0;
+}
+
+void nidx_shard_destroy(nidx_shard_comm* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    c->local.release(); c->gathered.release(); c->total.release();
+    delete c;
+}
+
+int nidx_vec_set_paragraph_keys(nidx_vec_segment* s, const uint64_t* keys) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(s->cfg.device));
+    if (!keys) { cudaFree(s->d_par_keys); s->d_par_keys = nullptr; return 0; }
+    if (!s->d_par_keys) CU(cudaMalloc(&s->d_par_keys, std::max<size_t>(s->n_par, 1) * 8));
+    CU(cudaMemcpy(s->d_par_keys, keys, (size_t)s->n_par * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// common tail: all-gather the local part, merge, deliver
+static int shard_exchange_and_merge(nidx_shard_comm* c, int nq, int k, bool dedup, int with_duplicates, bool ohost, uint32_t* out_ids, float* out_scores,
+                                    int32_t* out_part, int32_t* out_counts, cudaStream_t stream) {
+    NcclApi& N = nccl_api();
+    size_t words = shard_part_words(nq, k, dedup);
+    uint32_t* local = c->local.as<uint32_t>();
+    uint32_t* gathered = c->gathered.as<uint32_t>();
+    NC(N.AllGather(local, gathered, words * 4, NCCL_INT8, c->comm, stream));
+    LAUNCHED();
+    // outputs: device pointers, or staged behind the gathered parts when the caller's are host pointers
+    uint32_t* d_ids = out_ids; float* d_sc = out_scores; int* d_part = out_part; int* d_cnt = out_counts;
+    if (ohost) {
+        uint32_t* stage = gathered + (size_t)c->world * words;
+        d_ids = stage; d_sc = reinterpret_cast<float*>(stage + (size_t)nq * k); d_part = reinterpret_cast<int*>(stage + 2 * (size_t)nq * k);
+        d_cnt = reinterpret_cast<int*>(stage + 3 * (size_t)nq * k);
+    }
+    if (dedup) {
+        size_t per = (size_t)k * 16 + (size_t)c->world * k * 8;
+        int threads = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(96 * 1024) / per));
+        if (per > 96 * 1024) return fail(NIDX_EINVAL, "k = %d is too large for the de-duplicating merge over %d parts", k, c->world);
+        threads = std::min(threads, nq);
+        size_t smem = per * threads;
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(shard_fssc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shard_fssc_kernel<<<(nq + threads - 1) / threads, threads, smem, stream>>>(gathered, c->world, words, nq, k, with_duplicates, d_ids, d_sc, d_part, d_cnt);
+        LAUNCHED();
+    } else {
+        if (k > 1024 || (long long)c->world * k >= (1ll << 31)) return fail(NIDX_EINVAL, "k above 1024 not supported");
+        int cap = topk_cap(k, 256);
+        if ((size_t)cap * 8 > 48 * 1024) CU(cudaFuncSetAttribute(parts_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
+        parts_merge_kernel<<<nq, 256, (size_t)cap * 8, stream>>>(gathered, reinterpret_cast<const float*>(gathered + (size_t)nq * k), c->world, words, nq, k, cap, d_ids,
+                                                                  d_sc, d_part);
+        LAUNCHED();
+        if (d_cnt) {
+            shard_count_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(d_ids, nq, k, d_cnt);
+            LAUNCHED();
+        }
+    }
+    CU(cudaGetLastError());
+    if (ohost) {
+        CU(cudaMemcpyAsync(out_ids, d_ids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_scores, d_sc, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+        if (out_part) CU(cudaMemcpyAsync(out_part, d_part, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
+        if (out_counts) CU(cudaMemcpyAsync(out_counts, d_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    return 0;
+}
+
+int nidx_vec_search_sharded(nidx_shard_comm* c, nidx_vec_segment* seg, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p,
+                            int32_t dedup, uint32_t* out_ids, float* out_scores, int32_t* out_part, int32_t* out_counts, void* stream_) {
+    if (!c || !seg || !p || !out_ids || !out_scores) return fail(NIDX_EINVAL, "null argument");
+    if (nq <= 0) return 0;
+    if (seg->cfg.device != c->device) return fail(NIDX_EINVAL, "segment on device %d, communicator on device %d", seg->cfg.device, c->device);
+    int k = p->k;
+    if (k <= 0) return fail(NIDX_EINVAL, "k must be positive");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    bool host = mem == NIDX_MEM_HOST;
+    std::lock_guard<std::mutex> lock(c->mu);
+    size_t words = shard_part_words(nq, k, dedup != 0);
+    ENSURE(c->local, words * 4 + (size_t)nq * 4);
+    ENSURE(c->gathered, (size_t)c->world * words * 4 + (size_t)nq * k * 12 + (size_t)nq * 4 + 64);
+    uint32_t* local = c->local.as<uint32_t>();
+    int* local_cnt = reinterpret_cast<int*>(local + words);
+    // 1. this rank's segment: queries from the caller's memory, results straight into the exchange record
+    int r = vec_search_impl(seg, queries, nq, ldq, host, false, p, local, reinterpret_cast<float*>(local + (size_t)nq * k), local_cnt, stream);
+    if (r) return r;
+    if (dedup) {
+        int n_res = nq * k;
+        shard_keys_kernel<<<(n_res * 32 + 255) / 256, 256, 0, stream>>>(seg->vdev(), local, n_res, seg->d_par_keys, (uint32_t)c->rank, p->with_duplicates ? 0 : 1,
+                                                                       reinterpret_cast<uint64_t*>(local + 2 * (size_t)nq * k),
+                                                                       reinterpret_cast<uint64_t*>(local + 4 * (size_t)nq * k));
+        LAUNCHED();
+    }
+    // 2. + 3. exchange and merge
+    r = shard_exchange_and_merge(c, nq, k, dedup != 0, p->with_duplicates, host, out_ids, out_scores, out_part, out_counts, stream);
+    if (r) return r;
+    if (host) CU(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int nidx_txt_search_sharded(nidx_shard_comm* c, nidx_txt_segment* seg, const uint32_t* query_terms, const uint32_t* query_off, int32_t nq, int mem,
+                            const nidx_txt_search_params* p, uint32_t* out_docs, float* out_scores, int32_t* out_part, int32_t* out_counts, uint64_t* out_total,
+                            void* stream_) {
+    if (!c || !seg || !p || !out_docs || !out_scores) return fail(NIDX_EINVAL, "null argument");
+    if (nq <= 0) return 0;
+    if (seg->device != c->device) return fail(NIDX_EINVAL, "segment on device %d, communicator on device %d", seg->device, c->device);
+    int k = p->k;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    bool host = mem == NIDX_MEM_HOST;
+    std::lock_guard<std::mutex> lock(c->mu);
+    NcclApi& N = nccl_api();
+    size_t words = shard_part_words(nq, k, false);
+    ENSURE(c->local, words * 4 + (size_t)nq * 4);
+    ENSURE(c->gathered, (size_t)c->world * words * 4 + (size_t)nq * k * 12 + (size_t)nq * 4 + 64);
+    ENSURE(c->total, (size_t)nq * 8);
+    uint32_t* local = c->local.as<uint32_t>();
+    int* local_cnt = reinterpret_cast<int*>(local + words);
+    uint64_t* d_total = host ? c->total.as<uint64_t>() : (out_total ? out_total : c->total.as<uint64_t>());
+    // the min_score cut is applied to the merged list by the caller's convention (reader.rs:302-305 drops below min_score after top-k):
+    // every part applies it locally, which commutes with the merge.
+    int r = txt_search_impl(seg, query_terms, query_off, nq, host, false, p, local, reinterpret_cast<float*>(local + (size_t)nq * k), local_cnt, d_total, stream);
+    if (r) return r;
+    NC(N.AllReduce(d_total, d_total, (size_t)nq, NCCL_UINT64, NCCL_SUM, c->comm, stream));   // Count collector over all parts
+    LAUNCHED();
+    r = shard_exchange_and_merge(c, nq, k, false, 1, host, out_docs, out_scores, out_part, out_counts, stream);
+    if (r) return r;
+    if (host) {
         if (out_total) CU(cudaMemcpyAsync(out_total, d_total, (size_t)nq * 8, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
     }

@@ -57,8 +57,12 @@ struct BlockTopK {
             int pos = atomicAdd(count, 1);
             buf[pos] = key;  // cap >= k + blockDim.x and count <= k after a flush
         }
+        // The flush decision must be the same in every thread: the count is read between two barriers, so no thread can
+        // reach the next round's atomicAdd before all threads have read it (flush() contains barriers).
         __syncthreads();
-        if (*count > cap - (int)blockDim.x) flush();
+        int c = *count;
+        __syncthreads();
+        if (c > cap - (int)blockDim.x) flush();
     }
     // Final: sorted best-k in buf[0..min(count,k)).
     __device__ int finish() {

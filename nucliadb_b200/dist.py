@@ -151,3 +151,112 @@ class ShardedTextSearcher(ShardedSearcher):
         slot["work_total"].wait()
         slot["work_total"] = None
         return (*merged, slot["total"])
+
+
+class ShardComm:
+    """nidx_shard_comm: the library's own NCCL communicator (include/nidx_b200.h "Segments sharded over the GPUs of one node").
+    The 128-byte NCCL id is created by rank 0 inside the library and handed to the other ranks through `exchange`, any
+    callable that returns rank 0's bytes on every rank -- by default a broadcast over the already initialised
+    torch.distributed group (any backend: the id is host data)."""
+
+    def __init__(self, rank: int, world: int, device: int, exchange=None):
+        import ctypes as C
+
+        from . import _lib
+
+        L = _lib.require_device()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(L.nidx_shard_unique_id(buf))
+        payload = bytes(buf)
+        if exchange is None:
+            import torch.distributed as dist
+
+            box = [payload]
+            dist.broadcast_object_list(box, src=0)
+            payload = box[0]
+        else:
+            payload = exchange(payload)
+        ident = (C.c_uint8 * 128).from_buffer_copy(payload)
+        self._h = C.c_void_p()
+        _lib.check(L.nidx_shard_init(ident, C.c_int32(rank), C.c_int32(world), C.c_int32(device), C.byref(self._h)))
+        self.rank, self.world, self.device = rank, world, device
+
+    def close(self):
+        from . import _lib
+
+        if self._h is not None:
+            _lib.load().nidx_shard_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search_vectors(self, segment, queries, k, ef=0, min_score=-1.0, with_duplicates=True, method=None, dedup=False, out=None, stream=None):
+        """nidx_vec_search_sharded: -> (ids local to their part, scores, part, counts), identical on every rank.  torch CUDA
+        queries: device path, asynchronous on the current stream; numpy queries: host path (copies inside the call)."""
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib
+        from .segment import _is_torch, _torch_stream
+
+        L = _lib.load()
+        p = _lib.VecSearchParams(k, ef, min_score, int(with_duplicates), _lib.NIDX_METHOD_HNSW if method is None else method, None, 0)
+        if _is_torch(queries):
+            import torch
+
+            nq, ldq = queries.shape
+            dev = queries.device
+            if out is None:
+                out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+                       torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq,), dtype=torch.int32, device=dev))
+            _lib.check(L.nidx_vec_search_sharded(self._h, segment._h, _lib.ptr(queries), C.c_int32(nq), C.c_int32(ldq), _lib.NIDX_MEM_DEVICE, C.byref(p),
+                                                 C.c_int32(int(dedup)), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+                                                 _torch_stream(self.device)))
+            return out
+        queries = np.ascontiguousarray(np.atleast_2d(queries), dtype=np.float32)
+        nq, ldq = queries.shape
+        if out is None:
+            out = (np.empty((nq, k), dtype=np.uint32), np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int32), np.empty(nq, dtype=np.int32))
+        _lib.check(L.nidx_vec_search_sharded(self._h, segment._h, _lib.ptr(queries), C.c_int32(nq), C.c_int32(ldq), _lib.NIDX_MEM_HOST, C.byref(p),
+                                             C.c_int32(int(dedup)), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+                                             C.c_void_p(stream) if stream else None))
+        return out
+
+    def search_text(self, segment, query_terms, query_off, k, mode=0, use_tf=True, min_score=0.0, out=None):
+        """nidx_txt_search_sharded: -> (docs local to their part, scores, part, counts, total over all parts)."""
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib
+        from .segment import _is_torch, _torch_stream
+
+        L = _lib.load()
+        p = _lib.TxtSearchParams(k, mode, int(use_tf), min_score, 0, 0.0, 0, 0)
+        if _is_torch(query_terms):
+            import torch
+
+            nq = query_off.numel() - 1
+            dev = query_terms.device
+            if out is None:
+                out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+                       torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq,), dtype=torch.int32, device=dev),
+                       torch.empty((nq,), dtype=torch.int64, device=dev))
+            _lib.check(L.nidx_txt_search_sharded(self._h, segment._h, _lib.ptr(query_terms), _lib.ptr(query_off), C.c_int32(nq), _lib.NIDX_MEM_DEVICE, C.byref(p),
+                                                 _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]), _torch_stream(self.device)))
+            return out
+        query_terms = np.ascontiguousarray(query_terms, dtype=np.uint32)
+        query_off = np.ascontiguousarray(query_off, dtype=np.uint32)
+        nq = len(query_off) - 1
+        if out is None:
+            out = (np.empty((nq, k), dtype=np.uint32), np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int32), np.empty(nq, dtype=np.int32),
+                   np.empty(nq, dtype=np.uint64))
+        _lib.check(L.nidx_txt_search_sharded(self._h, segment._h, _lib.ptr(query_terms), _lib.ptr(query_off), C.c_int32(nq), _lib.NIDX_MEM_HOST, C.byref(p),
+                                             _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]), None))
+        return out

@@ -118,6 +118,11 @@ class VectorSegment:
     def set_alive(self, alive_bits: Optional[np.ndarray]):
         check(_lib.load().nidx_vec_set_alive(self._h, ptr(alive_bits), _lib.NIDX_MEM_HOST))
 
+    def set_paragraph_keys(self, keys: Optional[np.ndarray]):
+        """64-bit keys of the paragraph ids, for the cross-segment de-duplication of a sharded search (Fssc, searcher.rs:150-199)."""
+        keys = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+        check(_lib.load().nidx_vec_set_paragraph_keys(self._h, ptr(keys)))
+
     # ---- search ----------------------------------------------------------------------------------------
     def search(self, queries, k: int, ef: int = 0, min_score: float = -1.0, with_duplicates=True, method=_lib.NIDX_METHOD_AUTO,
                filter_bits=None, filter_matching: int = 0, out=None, stream: Optional[int] = None):
@@ -247,6 +252,11 @@ class TextSegment:
         check(L.nidx_txt_search(self._h, ptr(query_terms), ptr(query_off), C.c_int32(nq), _lib.NIDX_MEM_HOST, C.byref(p), ptr(docs), ptr(scores), ptr(counts),
                                 ptr(total), None))
         return docs, scores, counts, total
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(_lib.load().nidx_txt_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def close(self):
         if self._h is not None:

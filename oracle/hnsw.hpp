@@ -153,9 +153,15 @@ static inline float sim_to(const Data& D, const Query& q, uint32_t x, Counters* 
 
 // hnsw/search.rs:242-304.  Returns results sorted descending.  `score(x)` is Retriever::similarity_upper_bound(x, query).score:
 // the exact similarity for a dense query, the RaBitQ estimate for a quantised one (segment.rs:339-348).
-template <class ScoreFn>
+// `will_need(y)` is the reference's preload pass (search.rs:276-281: Retriever::will_need_vector on every unvisited neighbour
+// before the first similarity; an madvise(MADV_WILLNEED) there, vector_store.rs:91-110).  The restatement issues software
+// prefetches instead, so that the CPU baseline overlaps the neighbours' memory latencies as the reference's page-cache
+// read-ahead does; it cannot change a result.
+struct NoPreload { void operator()(uint32_t) const {} };
+template <class ScoreFn, class PreloadFn = NoPreload>
 static inline std::vector<Scored> layer_search_with(uint32_t n, const GraphView& G, ScoreFn score, int layer, size_t k,
-                                                    const std::vector<uint32_t>& entry_points, Scratch& sc, Counters* cnt) {
+                                                    const std::vector<uint32_t>& entry_points, Scratch& sc, Counters* cnt,
+                                                    PreloadFn will_need = PreloadFn()) {
     auto worse_first = [](const Scored& a, const Scored& b) { return better(a, b); };   // min-heap on rank
     auto better_first = [](const Scored& a, const Scored& b) { return better(b, a); };  // max-heap on rank
     std::priority_queue<Scored, std::vector<Scored>, decltype(better_first)> candidates(better_first);
@@ -175,6 +181,11 @@ static inline std::vector<Scored> layer_search_with(uint32_t n, const GraphView&
         if (cnt) cnt->n_expand++;
         const uint32_t* edges = G.row(c.id, layer);
         int stride = G.stride(layer);
+        for (int e = 0; e < stride; ++e) {  // 276-281: preload pass over the unvisited neighbours
+            uint32_t y = edges[e];
+            if (y == NIL) break;
+            if (!sc.test(y)) will_need(y);
+        }
         for (int e = 0; e < stride; ++e) {
             uint32_t y = edges[e];
             if (y == NIL) break;
@@ -197,7 +208,13 @@ static inline std::vector<Scored> layer_search_with(uint32_t n, const GraphView&
 }
 static inline std::vector<Scored> layer_search(const Data& D, const GraphView& G, const Query& q, int layer, size_t k,
                                                const std::vector<uint32_t>& entry_points, Scratch& sc, Counters* cnt) {
-    return layer_search_with(D.n, G, [&](uint32_t x) { return sim_to(D, q, x, cnt); }, layer, k, entry_points, sc, cnt);
+    // HnswSearcher::new(&retriever, true) on the query path (segment.rs:540); the builder passes false (build.rs:41), where the
+    // prefetches are harmless.  One prefetch per 64-byte line of the row, into L2 (32 rows of 3 KB exceed L1).
+    auto preload = [&](uint32_t y) {
+        const char* p = reinterpret_cast<const char*>(D.vec(y));
+        for (size_t off = 0; off < (size_t)D.d * 4; off += 64) __builtin_prefetch(p + off, 0, 2);
+    };
+    return layer_search_with(D.n, G, [&](uint32_t x) { return sim_to(D, q, x, cnt); }, layer, k, entry_points, sc, cnt, preload);
 }
 
 // hnsw/search.rs:135-171 NodeFilter + 388-412 RepCounter.

@@ -89,16 +89,55 @@ def test_bm25_min_score_alive_and_missing_terms():
     assert (d3[0, : c3[0]] == d0[0, : c3[0]]).all()
 
 
-def test_bm25_term_major_variant_matches(monkeypatch):
-    """The experimental term-major kernel (NIDX_B200_BM25=tm) must give the same answers as the default one."""
-    P = corpus(40000, 3000, seed=17)
+def check_against_oracle(P, queries, k, mode, use_tf, **kw):
+    docs, sc, cnt, total = run(P, queries, k, mode, use_tf, **kw)
+    od, osc, oc, otot = O.bm25_search(P, queries, k, mode=mode, use_tf=use_tf, nthreads=4)
+    assert (total == otot).all() and (cnt == oc).all()
+    assert np.allclose(sc, osc, rtol=1e-5, atol=1e-5)
+    for q in range(len(queries)):   # the same documents wherever the oracle's k-th score is separated from the next
+        c = cnt[q]
+        if c and (c < k or True):
+            assert set(docs[q, :c].tolist()) == set(od[q, :c].tolist()) or abs(osc[q, c - 1] - osc[q, max(c - 2, 0)]) < 2e-5
+    return docs, sc, cnt, total
+
+
+def test_bm25_dense_tiles_fall_back_to_fine_tiles():
+    """Few documents, long documents, frequent terms: a fine tile (4096 docs) holds far more postings than the accumulator
+    table has slots, so the tile span drops to one fine tile and pass 1 takes the block-per-run path (more chunks than the
+    chunk map holds)."""
+    P = corpus(30000, 60, seed=21, mean_len=120)
+    rng = np.random.default_rng(4)
+    queries = [list(rng.choice(60, 40, replace=False)) for _ in range(6)]
+    check_against_oracle(P, queries, 100, _lib.NIDX_BM25_OR, True)
+    check_against_oracle(P, queries, 100, _lib.NIDX_BM25_OR, False)
+    check_against_oracle(P, [q[:3] for q in queries], 100, _lib.NIDX_BM25_AND, True)
+
+
+def test_bm25_sparse_query_spans_many_fine_tiles_per_tile():
+    """Rare terms over many documents: one tile covers many fine tiles (terms without a skip row are walked linearly), and the
+    threshold-crossing candidate list carries the top-k from tile to tile."""
+    P = corpus(300000, 40000, seed=23, mean_len=30)
+    df = np.diff(P.term_off.astype(np.int64))
+    rng = np.random.default_rng(5)
+    rare = np.nonzero((df >= 3) & (df < 200))[0]
+    mid = np.nonzero(df >= 300)[0]
+    queries = [list(rng.choice(rare, 30, replace=False)) for _ in range(8)] + [list(rng.choice(mid, 20, replace=False)) for _ in range(8)]
+    queries += [list(rng.choice(rare, 10, replace=False)) + list(rng.choice(mid, 10, replace=False)) for _ in range(8)]
+    check_against_oracle(P, queries, 100, _lib.NIDX_BM25_OR, False)
+    check_against_oracle(P, queries, 10, _lib.NIDX_BM25_OR, True)
+    check_against_oracle(P, [[int(q[-1]), int(q[-2])] for q in queries[8:]], 50, _lib.NIDX_BM25_AND, True)
+
+
+def test_bm25_table_size_does_not_change_results(monkeypatch):
+    """NIDX_B200_BM25_BITS selects a larger accumulator table (other tile spans, other hash placement): bit-identical output."""
+    P = corpus(120000, 3000, seed=17)
     rng = np.random.default_rng(2)
     queries = [list(rng.choice(300, 10, replace=False) + 10) for _ in range(24)]
     base = run(P, queries, 50, _lib.NIDX_BM25_OR, True)
-    monkeypatch.setenv("NIDX_B200_BM25", "tm")
-    tm = run(P, queries, 50, _lib.NIDX_BM25_OR, True)
-    assert (base[0] == tm[0]).all() and np.array_equal(base[1], tm[1]) and (base[2] == tm[2]).all() and (base[3] == tm[3]).all()
-    tm_and = run(P, [q[:3] for q in queries], 50, _lib.NIDX_BM25_AND, True)
-    monkeypatch.delenv("NIDX_B200_BM25")
     base_and = run(P, [q[:3] for q in queries], 50, _lib.NIDX_BM25_AND, True)
-    assert (base_and[0] == tm_and[0]).all() and np.array_equal(base_and[1], tm_and[1]) and (base_and[3] == tm_and[3]).all()
+    for bits in ("14", "15"):
+        monkeypatch.setenv("NIDX_B200_BM25_BITS", bits)
+        other = run(P, queries, 50, _lib.NIDX_BM25_OR, True)
+        assert all(np.array_equal(a, b) for a, b in zip(base, other))
+        other_and = run(P, [q[:3] for q in queries], 50, _lib.NIDX_BM25_AND, True)
+        assert all(np.array_equal(a, b) for a, b in zip(base_and, other_and))

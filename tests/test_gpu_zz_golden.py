@@ -9,10 +9,7 @@ import pytest
 import oracle as O
 from test_golden_fixtures import BM25_CASES, load, postings_of
 
-# Written after this round's GPU budget was spent: they have passed against an oracle-backed stand-in of the device API on CPU
-# but have not run on hardware yet, so they are opt-in until they have (set NIDX_B200_UNVERIFIED_GPU_TESTS=1).
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("NIDX_B200_UNVERIFIED_GPU_TESTS") != "1",
-                                                  reason="not yet run on a GPU box; set NIDX_B200_UNVERIFIED_GPU_TESTS=1")]
+pytestmark = pytest.mark.gpu
 
 
 def test_cuda_path_reproduces_the_vector_fixture():

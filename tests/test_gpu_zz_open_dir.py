@@ -8,11 +8,7 @@ import pytest
 
 from nucliadb_b200 import vector as V
 
-# Written after this round's GPU budget was spent: it passes on the oracle-backed emulation of the C ABI
-# (tests/test_mirror_on_emulator.py) but has not run on hardware yet, so it is opt-in until it has
-# (set NIDX_B200_UNVERIFIED_GPU_TESTS=1).
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("NIDX_B200_UNVERIFIED_GPU_TESTS") != "1",
-                                                  reason="not yet run on a GPU box; set NIDX_B200_UNVERIFIED_GPU_TESTS=1")]
+pytestmark = pytest.mark.gpu
 
 RID = "9cb39c75f8d9498d8f82d92b173011f5"
 

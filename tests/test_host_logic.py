@@ -100,50 +100,44 @@ def test_stored_paragraph_bytes_and_store_round_trip(tmp_path):
         PS.read_paragraphs(str(tmp_path))
 
 
-# ---- the posting-to-lane assignment of the warp-chunked BM25 kernel variants (csrc/bm25_w.cuh), restated in Python -----------------
-def test_warp_chunked_assignment_covers_every_posting_once():
-    """bm25_w_kernel<THREADS, ROUND>: in the round starting at flattened index `base`, warp w / lane l / slot u handles
-    i = base + w * (ROUND * 32) + u * 32 + l; the term is found by one binary search for slot 0 (`locate`) and by walking forward
-    for the next slots (`walk`).  Every flattened posting of a tile must be visited exactly once and land on the (term, offset)
-    the per-posting binary search of bm25_kernel gives."""
+# ---- the chunk map of bm25_kernel (csrc/bm25.cuh resolve()), restated in Python --------------------------------------------------
+def test_bm25_chunk_map_covers_every_posting_once():
+    """resolve(): run r of a tile has ceil(len_r / 32) chunks; pre[] is the exclusive prefix of the chunk counts in TERM order
+    (the warp scans lanes, then carries over the 32-term groups), chunk_run[g] names the run of chunk g.  In pass 1 warp w takes
+    chunks w, w + 8, ... four at a time; lane l of chunk g handles posting (g - pre[r]) * 32 + l of run r.  Every posting of the
+    tile must be visited exactly once."""
     rng = np.random.default_rng(12)
-
-    def locate(pre, nt, i):                       # last term with pre[t] <= i
-        lo, r = 0, nt - 1
-        while lo < r:
-            m = (lo + r + 1) >> 1
-            if pre[m] <= i:
-                lo = m
-            else:
-                r = m - 1
-        return lo
-
-    for threads, rounds in ((128, 4), (256, 2)):
-        chunk, warps = rounds * 32, threads // 32
-        for trial in range(40):
-            nt = int(rng.integers(1, 129))
-            counts = rng.integers(0, 40, nt) * (rng.random(nt) < 0.7)          # many empty slices, as in a real tile
-            if trial == 0:
-                counts[:] = 0
-            pre = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
-            total = int(counts.sum())
-            seen = np.zeros(total, dtype=np.int64)
-            for base in range(0, max(total, 1), threads * rounds):
-                for w in range(warps):
+    warps, unroll = 8, 4
+    for trial in range(60):
+        nt = int(rng.integers(1, 129))
+        lens = (rng.integers(0, 200, nt) * (rng.random(nt) < 0.7)).astype(np.int64)
+        if trial == 0:
+            lens[:] = 0
+        chunks = (lens + 31) >> 5
+        pre = np.zeros(nt + 1, dtype=np.int64)
+        run = 0
+        for j in range(0, nt, 32):                       # the kernel's order: 32 terms per shuffle scan, carry `run`
+            c = chunks[j:j + 32]
+            pre[j:j + len(c)] = run + np.cumsum(c) - c
+            run += int(c.sum())
+        pre[nt] = run
+        chunk_run = np.full(max(run, 1), -1)
+        for r in range(nt):
+            chunk_run[pre[r]:pre[r] + chunks[r]] = r
+        seen = [np.zeros(n, dtype=np.int64) for n in lens]
+        for w in range(warps):
+            for g0 in range(w, run, warps * unroll):
+                for u in range(unroll):
+                    g = g0 + u * warps
+                    if g >= run:
+                        continue
+                    r = chunk_run[g]
+                    assert r >= 0
                     for lane in range(32):
-                        i0 = base + w * chunk + lane
-                        if i0 >= total:
-                            continue
-                        l = locate(pre, nt, i0)
-                        for u in range(rounds):
-                            i = i0 + u * 32
-                            if i >= total:
-                                break
-                            while l + 1 < nt and pre[l + 1] <= i:   # walk
-                                l += 1
-                            assert l == locate(pre, nt, i) and 0 <= i - pre[l] < counts[l]
-                            seen[i] += 1
-            assert (seen == 1).all()
+                        within = (g - pre[r]) * 32 + lane
+                        if within < lens[r]:
+                            seen[r][within] += 1
+        assert all((x == 1).all() for x in seen)
 
 
 # ---- bench.py's CPU-side pieces (they run on the GPU box's host cores; exercised here on a small graph) -----------------------------
