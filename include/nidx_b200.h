@@ -45,6 +45,9 @@ extern "C" {
 #define NIDX_METHOD_HNSW 1   /* hnsw/search.rs:306-383 */
 #define NIDX_METHOD_BRUTE 2  /* segment.rs:569-623 */
 #define NIDX_METHOD_BRUTE_RABITQ 3 /* segment.rs:581-608 with a RaBitQ query: quantised scan + exact rerank (rabitq.rs:222-244) */
+#define NIDX_METHOD_HNSW_RABITQ 4  /* hnsw/search.rs:306-383 with a RaBitQ query: the walk ranks by the estimate, layer 0 returns
+                                      min(100 k, 2000) nodes, rerank_top + closest_up_nodes on exact similarities.  What AUTO takes
+                                      when the segment carries codes (segment.rs:506-513) and the cost model picks the graph */
 
 #define NIDX_NIL 0xFFFFFFFFu
 
@@ -158,13 +161,16 @@ int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, in
 /* Counters of the last HNSW search / build on this segment (for the roofline accounting,
  * SURVEY 8d): [0] similarity evaluations, [1] node expansions, [2] visited-set overflows. */
 int nidx_vec_counters(nidx_vec_segment* seg, uint64_t out[3]);
+/* The same with the quantised walk's: [0] exact similarities computed, [1] expansions, [2] visited-set overflows, [3] closest_up
+ * overflows, [4] RaBitQ estimates, [5] exact similarities the sequential rerank_top needed (<= the share of [0] spent there). */
+int nidx_vec_counters_ex(nidx_vec_segment* seg, uint64_t out[6]);
 
 /* RaBitQ 1-bit codes (vector_types/rabitq.rs; Dot similarity and dimension % 64 == 0 only, config.rs:170-173).
  * nidx_vec_rabitq_encode builds the reference's vectors.quant records ([f32 dot_quant_original][u32 sum_bits][dim/8 sign
  * bits], quant_vector_store.rs:29,57-60) in HBM; nidx_vec_rabitq_codes copies them out ([n][dim/8 + 8] bytes, host);
  * nidx_vec_rabitq_estimate evaluates QueryVector::similarity (estimate, error bound; rabitq.rs:202-218) of every stored
  * vector for nq queries into out_estimate / out_error [nq][n] (same `mem` as the queries).  NIDX_METHOD_BRUTE_RABITQ in
- * nidx_vec_search needs the codes.  The quantised HNSW walk (search.rs:332-366) is not implemented yet. */
+ * and NIDX_METHOD_HNSW_RABITQ in nidx_vec_search need the codes. */
 int nidx_vec_rabitq_encode(nidx_vec_segment* seg, void* stream);
 int nidx_vec_rabitq_codes(const nidx_vec_segment* seg, uint8_t* out_codes);
 int nidx_vec_rabitq_estimate(nidx_vec_segment* seg, const float* queries, int32_t nq, int32_t ldq, int mem, float* out_estimate, float* out_error,

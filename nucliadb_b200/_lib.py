@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libnidx_b200.so")
 
 NIDX_MEM_HOST, NIDX_MEM_DEVICE = 0, 1
 NIDX_SIM_DOT, NIDX_SIM_COSINE = 0, 1
-NIDX_METHOD_AUTO, NIDX_METHOD_HNSW, NIDX_METHOD_BRUTE, NIDX_METHOD_BRUTE_RABITQ = 0, 1, 2, 3
+NIDX_METHOD_AUTO, NIDX_METHOD_HNSW, NIDX_METHOD_BRUTE, NIDX_METHOD_BRUTE_RABITQ, NIDX_METHOD_HNSW_RABITQ = 0, 1, 2, 3, 4
 NIDX_BM25_OR, NIDX_BM25_AND = 0, 1
 NIL = 0xFFFFFFFF
 
@@ -22,7 +22,7 @@ SYMBOLS = [
     "nidx_last_error", "nidx_device_count", "nidx_launch_count",
     "nidx_vec_create", "nidx_vec_open", "nidx_vec_save", "nidx_vec_close", "nidx_vec_len", "nidx_vec_device_vectors",
     "nidx_use_hnsw", "nidx_hnsw_levels", "nidx_vec_build_hnsw", "nidx_vec_extend_hnsw", "nidx_vec_graph_dims", "nidx_vec_set_graph", "nidx_vec_get_graph", "nidx_vec_set_alive",
-    "nidx_vec_search", "nidx_merge_topk", "nidx_vec_counters", "nidx_vec_last_kernel_ms",
+    "nidx_vec_search", "nidx_merge_topk", "nidx_vec_counters", "nidx_vec_counters_ex", "nidx_vec_last_kernel_ms",
     "nidx_vec_rabitq_encode", "nidx_vec_rabitq_codes", "nidx_vec_rabitq_estimate",
     "nidx_txt_create", "nidx_txt_set_stats", "nidx_txt_set_alive", "nidx_txt_close", "nidx_txt_search", "nidx_txt_last_kernel_ms",
     "nidx_shard_unique_id", "nidx_shard_init", "nidx_shard_destroy", "nidx_vec_set_paragraph_keys", "nidx_vec_search_sharded", "nidx_txt_search_sharded",

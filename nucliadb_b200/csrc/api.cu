@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "hnsw_build.cuh"
 #include "hnsw_search.cuh"
+#include "hnsw_rabitq.cuh"
 #include "rabitq.cuh"
 #include "scan.cu"
 #include "scan_tc.cuh"
@@ -259,8 +260,8 @@ static int finish_create(nidx_vec_segment* s, const uint32_t* paragraph_of_host)
             CU(cudaMemcpy(s->d_par_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
         }
     }
-    CU(cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
-    CU(cudaMemset(s->d_counters, 0, 4 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&s->d_counters, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
     CU(cudaMalloc(&s->d_work_counter, 64));
     CU(cudaEventCreate(&s->ev_k0));
     CU(cudaEventCreate(&s->ev_k1));
@@ -396,6 +397,15 @@ int nidx_vec_get_graph(const nidx_vec_segment* s, uint8_t* level, uint32_t* adj0
     if (w0) CU(cudaMemcpy(w0, s->d_w0, n0 * 4, cudaMemcpyDeviceToHost));
     if (adjU && nu) CU(cudaMemcpy(adjU, s->d_adjU, nu * 4, cudaMemcpyDeviceToHost));
     if (wU && nu) CU(cudaMemcpy(wU, s->d_wU, nu * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int nidx_vec_counters_ex(nidx_vec_segment* s, uint64_t out[6]) {
+    if (!s || !out) return fail(NIDX_EINVAL, "null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    unsigned long long h[8];
+    CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) out[i] = h[i];
     return 0;
 }
 
@@ -548,6 +558,18 @@ static hs_kernel_t pick_search_kernel(int ld) {
     return hnsw_search_kernel<0>;
 }
 
+static hs_kernel_t pick_rabitq_walk_kernel(int ld) {
+    if (ld % 128 == 0) switch (ld / 128) {
+        case 2: return hnsw_rabitq_kernel<2>;
+        case 3: return hnsw_rabitq_kernel<3>;
+        case 4: return hnsw_rabitq_kernel<4>;
+        case 6: return hnsw_rabitq_kernel<6>;
+        case 8: return hnsw_rabitq_kernel<8>;
+        default: break;
+    }
+    return hnsw_rabitq_kernel<0>;
+}
+
 typedef void (*scan_kernel_t)(VecDev, const float*, const float*, int, int, float*);
 static scan_kernel_t pick_scan_kernel(int ld) {
     if (ld % 128 == 0) switch (ld / 128) {
@@ -643,14 +665,15 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         if (!s->has_graph) method = NIDX_METHOD_BRUTE;
         else if (matching == 0 && p->filter_bits) method = NIDX_METHOD_BRUTE;
         else {
-            // the quantised scan serves single-vector Dot segments that carry codes (segment.rs:506-513); the HNSW walk itself is the
-            // dense one either way (the quantised walk is not implemented: results are at least as exact)
-            bool quant_ok = s->d_quant && !s->d_par_first && k <= 1024 && s->cfg.similarity == NIDX_SIM_DOT;
-            if (use_hnsw_cost(s->n_par, matching, (size_t)k, (size_t)s->cfg.m, quant_ok)) method = NIDX_METHOD_HNSW;
-            else method = quant_ok ? NIDX_METHOD_BRUTE_RABITQ : NIDX_METHOD_BRUTE;
+            // a segment that carries codes is searched with a RaBitQ query on either path (segment.rs:506-513: `rabitq` =
+            // has_quantized): the quantised walk (hnsw/search.rs:332-366) or the quantised scan (segment.rs:581-608)
+            bool walk_ok = s->d_quant && s->cfg.similarity == NIDX_SIM_DOT;
+            bool scan_ok = walk_ok && !s->d_par_first && k <= 1024;
+            if (use_hnsw_cost(s->n_par, matching, (size_t)k, (size_t)s->cfg.m, walk_ok)) method = walk_ok ? NIDX_METHOD_HNSW_RABITQ : NIDX_METHOD_HNSW;
+            else method = scan_ok ? NIDX_METHOD_BRUTE_RABITQ : NIDX_METHOD_BRUTE;
         }
     }
-    if (method == NIDX_METHOD_HNSW && !s->has_graph) return fail(NIDX_ESTATE, "HNSW search requested but the segment has no graph");
+    if ((method == NIDX_METHOD_HNSW || method == NIDX_METHOD_HNSW_RABITQ) && !s->has_graph) return fail(NIDX_ESTATE, "HNSW search requested but the segment has no graph");
 
     // outputs
     uint32_t* d_ids = out_ids; float* d_sc = out_scores; int* d_cnt = out_counts;
@@ -744,6 +767,52 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
             LAUNCHED();
         }
         CU(cudaGetLastError());
+    } else if (method == NIDX_METHOD_HNSW_RABITQ) {
+        // hnsw/search.rs:306-383 with SearchVector::RabitQ: estimate-ranked walk, k * 100 layer-0 results, exact rerank + closest_up
+        int rr = rabitq_check(s);
+        if (rr) return rr;
+        if (!s->d_quant) return fail(NIDX_ESTATE, "segment has no RaBitQ codes (call nidx_vec_rabitq_encode)");
+        int nw = s->d / 32;
+        size_t plane_bytes = (size_t)nq * 4 * nw * 4;
+        ENSURE(w.misc, ((plane_bytes + 15) / 16) * 16 + (size_t)nq * sizeof(RabitqQueryParams) + 64);
+        uint32_t* planes = w.misc.as<uint32_t>();
+        RabitqQueryParams* params = reinterpret_cast<RabitqQueryParams*>(w.misc.as<unsigned char>() + ((plane_bytes + 15) / 16) * 16);
+        rabitq_query_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(dq, s->ld, s->d, nq, planes, params);
+        LAUNCHED();
+        int last_k = (int)std::min<size_t>((size_t)k * 100, 2000);              // rabitq.rs:34-36 RERANKING_FACTOR / RERANKING_LIMIT
+        int cu_cap = std::min(std::max(k + k * s->s0, 2 * k), 4096);
+        int list_cap = std::max(last_k, cu_cap);
+        int slots = next_pow2(std::max(2048, 4 * cu_cap));
+        int hash_bits = ilog2(slots);
+        int gv_bits = 16;                                                       // 64 k slots: layer 0 visits ~10-20 k nodes at k = 10
+        while ((1 << gv_bits) < 24 * last_k) ++gv_bits;
+        if (const char* e = getenv("NIDX_B200_RQ_VISITED_BITS")) { int b = atoi(e); if (b >= 12 && b <= 22) gv_bits = b; }
+        size_t smem = rq_smem_bytes(s->ld, s->d, list_cap, hash_bits, k);
+        if (smem > 200 * 1024) return fail(NIDX_EINVAL, "quantised HNSW search needs %zu bytes of shared memory (k=%d, dim=%d): too large", smem, k, s->d);
+        hs_kernel_t kern = pick_rabitq_walk_kernel(s->ld);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HS_THREADS, smem));
+        int grid = std::min(nq, std::max(1, occ) * s->sm_count);
+        ENSURE(w.scores, ((size_t)grid << gv_bits) * 4);
+        SearchArgs a;
+        memset(&a, 0, sizeof(a));
+        a.mode = 0; a.nq = nq; a.queries = dq; a.qnorms = w.qnorms.as<float>(); a.k = k; a.ef0 = last_k; a.min_score = p->min_score;
+        a.with_duplicates = p->with_duplicates; a.multi_vector = s->cfg.multi_vector; a.filter = bits;
+        a.out_ids = d_ids; a.out_scores = d_sc; a.out_counts = d_cnt;
+        a.hash_bits = hash_bits; a.list_cap = list_cap; a.cu_cap = cu_cap;
+        a.codes = s->d_quant; a.code_stride = s->quant_stride; a.planes = planes; a.qparams = params;
+        a.gvisited = w.scores.as<uint32_t>(); a.gv_bits = gv_bits; a.last_k = last_k;
+        ENSURE(w.sched, 64);
+        a.work_counter = w.sched.as<unsigned int>();
+        a.counters = s->d_counters;
+        CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
+        CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        CU(cudaEventRecord(s->ev_k0, stream));
+        kern<<<grid, HS_THREADS, smem, stream>>>(V, s->gdev(), a);
+        CU(cudaEventRecord(s->ev_k1, stream));
+        LAUNCHED();
+        CU(cudaGetLastError());
     } else {
         int ef = p->ef > 0 ? p->ef : s->cfg.ef_search;
         int ef0 = std::max(k, ef);  // search.rs:338-345
@@ -762,7 +831,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         a.work_counter = w.sched.as<unsigned int>();
         a.counters = s->d_counters;
         CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
-        CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+        CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
         hs_kernel_t kern = pick_search_kernel(s->ld);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
@@ -925,7 +994,7 @@ static int run_insertions(nidx_vec_segment* s, const std::vector<uint8_t>& level
         int occ_rev = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_rev, reverse_link_kernel, HB_THREADS, smem_rev));
         int rev_grid = std::max(1, occ_rev) * s->sm_count;
-        CU(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+        CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
 
 
         VecDev V = s->vdev();

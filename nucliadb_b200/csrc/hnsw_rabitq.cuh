@@ -1,0 +1,339 @@
+// nidx_b200 — K5b: the HNSW walk with a RaBitQ query (sm_100a).  The reference's production path for Dot indexes that
+// carry 1-bit codes:
+//   nidx/nidx_vector/src/segment.rs:506-513       the query becomes SearchVector::RabitQ when the store has vectors.quant
+//   nidx/nidx_vector/src/hnsw/search.rs:306-383   HnswSearcher::search: the walk ranks by the ESTIMATE (similarity_upper_bound().score,
+//                                                 segment.rs:339-348), layer 0 asks for min(k * 100, 2000) nodes (search.rs:332-337),
+//                                                 rerank_top re-scores them exactly (rabitq.rs:222-244), closest_up_nodes and the
+//                                                 final sort run on exact similarities (search.rs:355-381)
+//   nidx/nidx_vector/src/vector_types/rabitq.rs:166-218   QueryVector::dot / similarity: 4 bit planes AND + POPC against the code
+//
+// One CTA per query (dynamic fetch, like hnsw_search_kernel, whose list / merge / closest_up code is reused).  What changes:
+//   * an expansion costs 32 codes of 112 bytes instead of 32 rows of 3 KB, so it is one warp's work: lane = neighbour.  The lane
+//     issues its code loads and its visited-set atomicCAS together -- codes of already visited neighbours are fetched for nothing
+//     (3.6 KB per expansion), but the two dependent latencies become one;
+//   * layer 0 keeps a 1 000-entry list (the reference's k * 100) and visits ~10-20 k nodes: the visited set of that layer is
+//     an open-addressing table in GLOBAL memory (one slice per resident CTA, L2 resident); upper layers and closest_up_nodes
+//     keep the shared-memory set;
+//   * rerank_top keeps the reference's SEQUENTIAL semantics (a candidate is evaluated iff `best.len() < k || best_k < upper
+//     bound` at its turn): chunks of 64 candidates are filtered against the state at the start of the chunk (a superset), their
+//     exact similarities are computed by the eight warps, one thread replays the reference's loop.
+// Estimates, error bounds and exact similarities are bit-identical to the oracle's (oracle/rabitq.hpp, hnsw_search_rabitq).
+#pragma once
+#include "hnsw_search.cuh"
+#include "rabitq.cuh"
+
+namespace nidx {
+
+constexpr int RQ_RC = 64;   // rerank chunk
+
+__host__ __device__ __forceinline__ size_t rq_smem_bytes(int ld, int d, int list_cap, int hash_bits, int k) {
+    return hs_smem_bytes(ld, list_cap, hash_bits) + (size_t)4 * (d / 32) * 4 + (size_t)RQ_RC * 12 + (size_t)(k + 1) * 8 + 64;
+}
+
+struct RqCtx {
+    const uint32_t* planes;   // shared memory, [4][nw]
+    int nw;
+    float low, delta, root_dim;
+    uint32_t sum_quantized;
+    uint32_t* gvis;           // this CTA's slice of the global visited table
+    uint32_t gv_mask;
+    int gv_bits, gv_limit;
+    unsigned long long n_quant, n_rerank;
+};
+
+// rabitq.rs:166-218 for the code at `code` (16-byte aligned, stride bytes, zero padded): (estimate, error bound)
+__device__ __forceinline__ void rq_estimate(const RqCtx& r, const unsigned char* __restrict__ code, int stride, float& estimate, float& error) {
+    const uint4* c4 = reinterpret_cast<const uint4*>(code);
+    uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, dqo_bits = 0, sum_bits = 0;
+    int nchunks = stride >> 4;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        uint4 w = __ldg(c4 + ch);
+        uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        if (ch == 0) { dqo_bits = w.x; sum_bits = w.y; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int i = ch * 4 + t - 2;
+            if (i >= 0 && i < r.nw) {
+                uint32_t s = ws[t];
+                d0 += __popc(r.planes[i] & s);
+                d1 += __popc(r.planes[r.nw + i] & s);
+                d2 += __popc(r.planes[2 * r.nw + i] & s);
+                d3 += __popc(r.planes[3 * r.nw + i] & s);
+            }
+        }
+    }
+    float dot = (float)(d0 + d1 * 2 + d2 * 4 + d3 * 8);
+    float dqo = __uint_as_float(dqo_bits);
+    float t1 = __fmul_rn(__fdiv_rn(__fmul_rn(2.0f, r.delta), r.root_dim), dot);
+    float t2 = __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, r.low), (float)sum_bits), r.root_dim);
+    float t3 = __fdiv_rn(__fmul_rn(r.delta, (float)r.sum_quantized), r.root_dim);
+    float t4 = __fmul_rn(r.low, r.root_dim);
+    float dqq = __fsub_rn(__fsub_rn(__fadd_rn(t1, t2), t3), t4);
+    estimate = __fdiv_rn(dqq, dqo);
+    float dd = __fmul_rn(dqo, dqo);
+    error = __fdiv_rn(__fmul_rn(__fsqrt_rn(__fdiv_rn(__fsub_rn(1.0f, dd), dd)), RABITQ_EPSILON), r.root_dim);
+}
+
+// Expand `node` ranking by the estimate.  Warp 0: lane = neighbour (visited test + code fetch + estimate + admission); the last
+// warp prefetches the adjacency row of the predicted next candidate (as hs_expand).  Leaves todo_key[0 .. stride) (0 = not
+// admitted), s_ntodo, s_nadmit, s_best_next for hs_merge<false>.
+template <bool GLOBAL_VIS>
+__device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, uint32_t node, int layer, int ef, int best) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int stride = G.stride(layer);
+    unsigned cur = c.hop & 1u;
+    if (warp == 0) {
+        const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
+        bool hit = c.pref_node[cur] == node;
+        const uint32_t* row = G.row(node, layer);
+        int len = *c.s_len;
+        uint64_t wkey = len >= ef ? c.A[len - 1] : 0;
+        int nadmit = 0, nfresh = 0;
+        bool ov = false;
+        for (int e0 = 0; e0 < stride; e0 += 32) {
+            uint32_t y = NIL;
+            if (e0 + lane < stride) y = hit ? prow[e0 + lane] : __ldg(row + e0 + lane);
+            bool valid = y != NIL, fresh = false;
+            float est = 0.0f, err = 0.0f;
+            if (valid) {
+                if (GLOBAL_VIS) {
+                    // the code loads inside rq_estimate do not depend on the CAS: both are in flight together
+                    uint32_t h = (y * 2654435761u) >> (32 - r.gv_bits);
+                    uint32_t old;
+                    bool full = *c.s_hash_count >= r.gv_limit;
+                    if (full) { ov = true; old = y; }
+                    else {
+                        while (true) {
+                            old = atomicCAS(&r.gvis[h], NIL, y);
+                            if (old == NIL || old == y) break;
+                            h = (h + 1) & r.gv_mask;
+                        }
+                    }
+                    rq_estimate(r, a.codes + (size_t)y * a.code_stride, a.code_stride, est, err);
+                    fresh = old == NIL;
+                } else {
+                    fresh = hash_insert(c, y, ov);
+                    if (fresh) rq_estimate(r, a.codes + (size_t)y * a.code_stride, a.code_stride, est, err);
+                }
+            }
+            uint64_t key = fresh ? make_key(est, y, 1) : 0;
+            bool admit = key > wkey;   // layer_search (search.rs:286): better than the worst of a full list (key 0 never is)
+            if (e0 + lane < stride) c.todo_key[e0 + lane] = admit ? key : 0;
+            nfresh += __popc(__ballot_sync(0xFFFFFFFFu, fresh));
+            nadmit += __popc(__ballot_sync(0xFFFFFFFFu, admit));
+        }
+        if (__any_sync(0xFFFFFFFFu, ov) && lane == 0) c.n_overflow++;
+        if (lane == 0) {
+            *c.s_ntodo = stride;
+            *c.s_hash_count += nfresh;
+            *c.s_best_next = INT_MAX;
+            *c.s_nadmit = nadmit;
+            c.n_expand++;
+            r.n_quant += nfresh;
+        }
+    } else if (warp == HS_WARPS - 1) {
+        int len = *c.s_len;
+        int pred = -1;
+        for (int i0 = best + 1; i0 < len && pred < 0; i0 += 32) {
+            int i = i0 + lane;
+            unsigned m = __ballot_sync(0xFFFFFFFFu, i < len && (c.A[i] & 1ull));
+            if (m) pred = i0 + __ffs(m) - 1;
+        }
+        uint32_t pnode = NIL;
+        if (pred >= 0) {
+            pnode = key_id(c.A[pred]);
+            const uint32_t* row2 = G.row(pnode, layer);
+            uint32_t* dst = c.pref_row + (cur ^ 1u) * HS_MAX_ROW;
+            for (int e = lane; e < stride; e += 32) cp_async4(dst + e, row2 + e);
+        }
+        if (lane == 0) c.pref_node[cur ^ 1u] = pnode;
+        cp_async_commit_wait_all();
+    }
+    c.hop++;
+    __syncthreads();
+}
+
+// Start a layer search on the list in c.A: every entry unexpanded, visited set = the list's ids.
+template <bool GLOBAL_VIS>
+__device__ inline void rq_reseed(SearchCtx& c, RqCtx& r) {
+    if (!GLOBAL_VIS) { hs_reseed(c); return; }
+    __syncthreads();
+    uint4 e4 = make_uint4(NIL, NIL, NIL, NIL);
+    for (uint32_t i = threadIdx.x; i < (r.gv_mask + 1) / 4; i += blockDim.x) reinterpret_cast<uint4*>(r.gvis)[i] = e4;
+    if (threadIdx.x == 0) { *c.s_hash_count = 0; *c.s_best = 0; c.pref_node[0] = NIL; c.pref_node[1] = NIL; }
+    __syncthreads();
+    int len = *c.s_len;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        uint64_t key = c.A[i] | 1ull;
+        c.A[i] = key;
+        uint32_t y = key_id(key), h = (y * 2654435761u) >> (32 - r.gv_bits);
+        while (true) {
+            uint32_t old = atomicCAS(&r.gvis[h], NIL, y);
+            if (old == NIL || old == y) break;
+            h = (h + 1) & r.gv_mask;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *c.s_hash_count = len;
+    __syncthreads();
+}
+
+template <bool GLOBAL_VIS>
+__device__ inline void rq_layer_search(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, int layer, int ef) {
+    while (true) {
+        int best = *c.s_best, len = *c.s_len;
+        if (best >= len) break;
+        uint64_t ckey = c.A[best];
+        rq_expand<GLOBAL_VIS>(G, c, a, r, key_id(ckey), layer, ef, best);
+        hs_merge<false>(c, ef, best);
+    }
+}
+
+template <int NG>
+__global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, GraphDev G, SearchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_ints[8];
+    __shared__ unsigned int s_work;
+    __shared__ int s_wtot[RQ_RC / 32], s_total, s_hlen;
+    __shared__ float s_best_k;
+    SearchCtx c;
+    RqCtx r;
+    unsigned char* p = smem;
+    c.qvec = reinterpret_cast<float*>(p); p += (size_t)V.ld * 4;
+    c.A = reinterpret_cast<uint64_t*>(p); p += (size_t)a.list_cap * 8;
+    c.B = reinterpret_cast<uint64_t*>(p); p += (size_t)a.list_cap * 8;
+    c.todo_key = reinterpret_cast<uint64_t*>(p); p += HS_MAX_ROW * 8;
+    c.hash = reinterpret_cast<uint32_t*>(p); p += (size_t)4 << a.hash_bits;
+    c.todo_id = reinterpret_cast<uint32_t*>(p); p += HS_MAX_ROW * 4;
+    c.pref_row = reinterpret_cast<uint32_t*>(p); p += 2 * HS_MAX_ROW * 4;
+    c.pref_node = reinterpret_cast<uint32_t*>(p); p += 16;
+    uint64_t* heap = reinterpret_cast<uint64_t*>(p); p += (size_t)(a.k + 1) * 8;          // rerank_top's `best`, rank keys, descending
+    uint32_t* planes = reinterpret_cast<uint32_t*>(p); p += (size_t)4 * (V.d / 32) * 4;
+    uint32_t* surv_id = reinterpret_cast<uint32_t*>(p); p += RQ_RC * 4;
+    float* surv_up = reinterpret_cast<float*>(p); p += RQ_RC * 4;
+    float* surv_real = reinterpret_cast<float*>(p);
+    c.hop = 0;
+    c.s_len = &s_ints[0]; c.s_best = &s_ints[1]; c.s_best_next = &s_ints[2]; c.s_ntodo = &s_ints[3];
+    c.s_hash_count = &s_ints[4]; c.s_flag = &s_ints[5]; c.s_nadmit = &s_ints[6];
+    c.hash_bits = a.hash_bits;
+    c.hash_mask = (1u << a.hash_bits) - 1;
+    c.hash_limit = (int)((15u << a.hash_bits) >> 4) - HS_MAX_ROW;
+    c.n_dist = c.n_expand = c.n_overflow = 0;
+    c.qnorm = 0.0f;
+    r.planes = planes; r.nw = V.d / 32; r.root_dim = __fsqrt_rn((float)V.d);
+    r.gvis = a.gvisited + ((size_t)blockIdx.x << a.gv_bits);
+    r.gv_bits = a.gv_bits; r.gv_mask = (1u << a.gv_bits) - 1; r.gv_limit = (int)((15u << a.gv_bits) >> 4) - HS_MAX_ROW;
+    r.n_quant = r.n_rerank = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ng = V.ld >> 2;
+    const RabitqQueryParams* qparams = reinterpret_cast<const RabitqQueryParams*>(a.qparams);
+
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_work = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        unsigned int q = s_work;
+        if (q >= (unsigned)a.nq) break;
+        const float* qsrc = a.queries + (size_t)q * V.ld;
+        for (int i = threadIdx.x; i < ng; i += blockDim.x) reinterpret_cast<float4*>(c.qvec)[i] = reinterpret_cast<const float4*>(qsrc)[i];
+        for (int i = threadIdx.x; i < 4 * r.nw; i += blockDim.x) planes[i] = a.planes[(size_t)q * 4 * r.nw + i];
+        RabitqQueryParams qp = qparams[q];
+        r.low = qp.low; r.delta = qp.delta; r.sum_quantized = qp.sum_quantized;
+        __syncthreads();
+
+        // entry point: similarity_upper_bound(ep, query).score = the estimate (search.rs:256-261)
+        if (threadIdx.x == 0) {
+            uint32_t ep = G.entry_node;
+            float est, err;
+            rq_estimate(r, a.codes + (size_t)ep * a.code_stride, a.code_stride, est, err);
+            c.A[0] = make_key(est, ep, 1);
+            *c.s_len = 1;
+            r.n_quant++;
+        }
+        __syncthreads();
+        for (int layer = (int)G.entry_layer; layer > 0; --layer) {   // search.rs:321-327: one best node per upper layer
+            rq_reseed<false>(c, r);
+            rq_layer_search<false>(G, c, a, r, layer, 1);
+            __syncthreads();
+        }
+        rq_reseed<true>(c, r);
+        rq_layer_search<true>(G, c, a, r, 0, a.last_k);             // search.rs:335-345
+        __syncthreads();
+
+        // ---- rerank_top (rabitq.rs:222-244) over the list, best estimate first ----
+        const int len = *c.s_len;
+        if (threadIdx.x == 0) { s_hlen = 0; s_best_k = 0.0f; }
+        __syncthreads();
+        for (int c0 = 0; c0 < len; c0 += RQ_RC) {
+            int hlen = s_hlen;
+            float best_k = s_best_k;
+            bool pass = false;
+            uint32_t id = NIL;
+            float up = 0.0f;
+            if (threadIdx.x < RQ_RC) {
+                int i = c0 + (int)threadIdx.x;
+                if (i < len) {
+                    id = key_id(c.A[i]);
+                    float est, err;
+                    rq_estimate(r, a.codes + (size_t)id * a.code_stride, a.code_stride, est, err);
+                    up = __fadd_rn(est, err);                               // EstimatedScore::new_with_error
+                    pass = hlen < a.k || best_k < up;
+                }
+                unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                if (lane == 0) s_wtot[warp] = __popc(m);
+            }
+            __syncthreads();
+            if (threadIdx.x < RQ_RC) {
+                unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+                int base = 0;
+                for (int w = 0; w < warp; ++w) base += s_wtot[w];
+                if (pass) { int pos = base + __popc(m & ((1u << lane) - 1)); surv_id[pos] = id; surv_up[pos] = up; }
+                if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < RQ_RC / 32; ++w) t += s_wtot[w]; s_total = t; }
+            }
+            __syncthreads();
+            int total = s_total;
+            for (int s = warp; s < total; s += HS_WARPS) {                  // exact similarities (Dot) of the survivors
+                float ab = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)surv_id[s] * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
+                if (lane == 0) { surv_real[s] = ab; c.n_dist++; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {                                          // the reference's loop, in order
+                for (int s = 0; s < total; ++s) {
+                    if (hlen < a.k || best_k < surv_up[s]) {
+                        r.n_rerank++;
+                        float real = surv_real[s];
+                        if (real >= a.min_score && (hlen < a.k || best_k < real)) {
+                            uint64_t key = make_key(real, surv_id[s], 0);
+                            int i = hlen;
+                            while (i > 0 && heap[i - 1] < key) { heap[i] = heap[i - 1]; --i; }
+                            heap[i] = key;
+                            if (hlen < a.k) ++hlen;          // else the worst (last) entry falls off
+                            best_k = key_score(heap[hlen - 1]);
+                        }
+                    }
+                }
+                s_hlen = hlen;
+                s_best_k = best_k;
+            }
+            __syncthreads();
+        }
+        // reranked (exact, descending) -> the list; closest_up_nodes + final sort on exact similarities (search.rs:369-381)
+        {
+            int hlen = s_hlen;
+            for (int i = threadIdx.x; i < hlen; i += blockDim.x) c.A[i] = heap[i];
+            if (threadIdx.x == 0) *c.s_len = hlen;
+            __syncthreads();
+        }
+        hs_emit_results<NG>(V, G, c, a, q);
+    }
+    if (lane == 0 && c.n_dist) atomicAdd(&a.counters[0], c.n_dist);
+    if (threadIdx.x == 0) {
+        if (c.n_expand) atomicAdd(&a.counters[1], c.n_expand);
+        if (c.n_overflow & 0xFFFFFFFFull) atomicAdd(&a.counters[2], c.n_overflow & 0xFFFFFFFFull);
+        if (c.n_overflow >> 32) atomicAdd(&a.counters[3], c.n_overflow >> 32);
+        if (r.n_quant) atomicAdd(&a.counters[4], r.n_quant);
+        if (r.n_rerank) atomicAdd(&a.counters[5], r.n_rerank);
+    }
+}
+
+}  // namespace nidx

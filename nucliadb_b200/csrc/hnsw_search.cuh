@@ -51,7 +51,15 @@ struct SearchArgs {
     int list_cap;            // >= max(ef0, efC) and >= cu_cap
     int cu_cap;              // closest_up_nodes pending-candidate capacity
     unsigned int* work_counter;       // dynamic query scheduler (zeroed by the host)
-    unsigned long long* counters;     // [0] similarities [1] expansions [2] visited overflows [3] cu overflows
+    unsigned long long* counters;     // [0] similarities [1] expansions [2] visited overflows [3] cu overflows [4] RaBitQ estimates [5] exact similarities the sequential rerank_top needs
+    // quantised walk (hnsw_rabitq.cuh; hnsw/search.rs:332-366 with SearchVector::RabitQ)
+    const unsigned char* codes;       // [n][code_stride] vectors.quant records
+    int code_stride;
+    const uint32_t* planes;           // [nq][4][d/32] query bit planes
+    const void* qparams;              // [nq] RabitqQueryParams
+    uint32_t* gvisited;               // [grid][1 << gv_bits] layer-0 visited table in global memory (L2)
+    int gv_bits;
+    int last_k;                       // min(k * RERANKING_FACTOR, RERANKING_LIMIT)
 };
 
 struct SearchCtx {
@@ -295,6 +303,37 @@ __device__ inline int hs_closest_up(const VecDev& V, const GraphDev& G, SearchCt
     return nacc;
 }
 
+// The tail of HnswSearcher::search for query q: closest_up_nodes on the list in c.A (search.rs:369-375), the final stable sort
+// (search.rs:381) and the NIL padding of the outputs.
+template <int NG>
+__device__ inline void hs_emit_results(const VecDev& V, const GraphDev& G, SearchCtx& c, const SearchArgs& a, unsigned int q) {
+    uint32_t* oi = a.out_ids + (size_t)q * a.k;
+    float* os = a.out_scores + (size_t)q * a.k;
+    int nacc = hs_closest_up<NG>(V, G, c, a, oi, os);
+    __syncthreads();
+    // search.rs:381 `filtered_result.sort_by(|a, b| b.1.total_cmp(&a.1))`: stable, descending.
+    // (closest_up_nodes can accept a late-found neighbour that outranks earlier results.)
+    {
+        uint32_t* tid = reinterpret_cast<uint32_t*>(c.B);
+        float* tsc = reinterpret_cast<float*>(c.B) + a.k;
+        for (int i = threadIdx.x; i < nacc; i += blockDim.x) { tid[i] = oi[i]; tsc[i] = os[i]; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+            uint32_t oi_bits = ordered_bits(tsc[i]);
+            int r = 0;
+            for (int j = 0; j < nacc; ++j) {
+                uint32_t oj = ordered_bits(tsc[j]);
+                r += (oj > oi_bits) || (oj == oi_bits && j < i);
+            }
+            oi[r] = tid[i];
+            os[r] = tsc[i];
+        }
+        __syncthreads();
+    }
+    for (int i = nacc + threadIdx.x; i < a.k; i += blockDim.x) { oi[i] = NIL; os[i] = 0.0f; }
+    if (threadIdx.x == 0) a.out_counts[q] = nacc;
+}
+
 template <int NG>
 __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, GraphDev G, SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -371,33 +410,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
         if (a.mode == 1 && threadIdx.x == 0)
             for (int layer = (int)G.entry_layer + 1; layer <= top && layer < HS_MAX_LAYERS; ++layer) a.found_count[(size_t)q * HS_MAX_LAYERS + layer] = 0;
 
-        if (a.mode == 0) {
-            uint32_t* oi = a.out_ids + (size_t)q * a.k;
-            float* os = a.out_scores + (size_t)q * a.k;
-            int nacc = hs_closest_up<NG>(V, G, c, a, oi, os);
-            __syncthreads();
-            // search.rs:381 `filtered_result.sort_by(|a, b| b.1.total_cmp(&a.1))`: stable, descending.
-            // (closest_up_nodes can accept a late-found neighbour that outranks earlier results.)
-            {
-                uint32_t* tid = reinterpret_cast<uint32_t*>(c.B);
-                float* tsc = reinterpret_cast<float*>(c.B) + a.k;
-                for (int i = threadIdx.x; i < nacc; i += blockDim.x) { tid[i] = oi[i]; tsc[i] = os[i]; }
-                __syncthreads();
-                for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
-                    uint32_t oi_bits = ordered_bits(tsc[i]);
-                    int r = 0;
-                    for (int j = 0; j < nacc; ++j) {
-                        uint32_t oj = ordered_bits(tsc[j]);
-                        r += (oj > oi_bits) || (oj == oi_bits && j < i);
-                    }
-                    oi[r] = tid[i];
-                    os[r] = tsc[i];
-                }
-                __syncthreads();
-            }
-            for (int i = nacc + threadIdx.x; i < a.k; i += blockDim.x) { oi[i] = NIL; os[i] = 0.0f; }
-            if (threadIdx.x == 0) a.out_counts[q] = nacc;
-        }
+        if (a.mode == 0) hs_emit_results<NG>(V, G, c, a, q);
     }
     // counters: n_dist lives in lane 0 of every warp, the rest in thread 0
     if (lane == 0 && c.n_dist) atomicAdd(&a.counters[0], c.n_dist);

@@ -180,6 +180,11 @@ class VectorSegment:
         check(_lib.load().nidx_vec_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def counters_ex(self):
+        out = (C.c_uint64 * 6)()
+        check(_lib.load().nidx_vec_counters_ex(self._h, out))
+        return dict(similarities=out[0], expansions=out[1], overflows=out[2] + out[3], estimates=out[4], rerank_needed=out[5])
+
     def counters(self):
         out = (C.c_uint64 * 3)()
         check(_lib.load().nidx_vec_counters(self._h, out))

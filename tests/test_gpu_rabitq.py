@@ -58,3 +58,65 @@ def test_rabitq_needs_dot_and_dim_multiple_of_64():
     seg = VectorSegment.create(make_vectors(100, 128, seed=1), 128, similarity=_lib.NIDX_SIM_COSINE)
     with pytest.raises(_lib.NidxError):
         seg.rabitq_encode()
+
+
+def _oracle_graph(seg, n, m, m0):
+    g = seg.get_graph()
+    og = O.Graph(n, m, m0, g["level"])
+    og.adj0[:], og.adjU[:] = g["adj0"], g["adjU"][: og.adjU.shape[0]]
+    og.entry_node, og.entry_layer = g["entry_node"], g["entry_layer"]
+    return og
+
+
+@pytest.mark.parametrize("d,n", [(128, 20000), (768, 6000)])
+def test_quantised_walk_matches_oracle(d, n):
+    """hnsw/search.rs:306-383 with a RaBitQ query: ids, scores and the number of estimates / expansions equal the oracle's
+    restatement on the same graph (oracle.hnsw_search_rabitq), with and without deletions, duplicates suppression and min_score."""
+    v = make_vectors(n, d, seed=61)
+    v[100:110] = v[90:100]                                   # byte-identical vectors for with_duplicates=False
+    q = make_queries(v, 24)
+    seg = VectorSegment.create(v, d, similarity=_lib.NIDX_SIM_DOT, m=16, m0=32, ef_construction=64)
+    seg.build_hnsw(seed=2, max_batch=512)
+    seg.rabitq_encode()
+    enc = O.rabitq_encode(v, nthreads=4)
+    og = _oracle_graph(seg, n, 16, 32)
+    for k, ms, dup in ((10, -1.0, True), (10, 0.2, True), (5, -1.0, False), (25, -1.0, True)):
+        ids, sc, cnt = seg.search(q, k, min_score=ms, with_duplicates=dup, method=_lib.NIDX_METHOD_HNSW_RABITQ)
+        c = seg.counters_ex()
+        oi, os_, oc, ocnt = O.hnsw_search_rabitq(v, enc, og, q, k, min_score=ms, with_duplicates=dup, nthreads=4)
+        assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+        # the kernel carries the entry point's estimate from layer to layer, the reference re-evaluates it in every layer_search
+        # (search.rs:256-261): entry_layer fewer estimates per query
+        assert c["estimates"] == int(ocnt[3]) - len(q) * og.entry_layer and c["expansions"] == int(ocnt[1]) and c["overflows"] == 0
+        assert c["similarities"] >= int(ocnt[0]) >= c["rerank_needed"] > 0   # exact similarities: the chunked filter may compute a few more
+    # deletions + filter: closest_up_nodes walks on until k alive results are found
+    alive = np.ones(n, dtype=bool)
+    alive[::3] = False
+    words = np.zeros((n + 63) // 64 * 8, dtype=np.uint8)
+    pb = np.packbits(alive, bitorder="little")
+    words[: len(pb)] = pb
+    bits = words.view(np.uint64)
+    seg.set_alive(bits)
+    ids, sc, cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_HNSW_RABITQ)
+    oi, os_, oc, _ = O.hnsw_search_rabitq(v, enc, og, q, 10, min_score=-1.0, filter_bits=bits, nthreads=4)
+    assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+    assert all(alive[i] for i in ids[ids != 0xFFFFFFFF])
+
+
+def test_auto_takes_the_quantised_walk_on_a_segment_with_codes():
+    """segment.rs:506-513 + 538: a segment that carries codes is searched with a RaBitQ query; on a large unfiltered segment the cost
+    model picks the graph, i.e. the quantised walk; recall against the exact scan stays high (the reference's recall test takes this
+    path: segment.rs:841-912)."""
+    n, d = 40000, 256
+    v = make_vectors(n, d, seed=62)
+    q = make_queries(v, 64)
+    seg = VectorSegment.create(v, d, similarity=_lib.NIDX_SIM_DOT, m=16, m0=32, ef_construction=100)
+    seg.build_hnsw(seed=2, max_batch=1024)
+    seg.rabitq_encode()
+    a_ids, a_sc, a_cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_AUTO)
+    est = seg.counters_ex()["estimates"]
+    w_ids, w_sc, w_cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_HNSW_RABITQ)
+    assert est > 0 and (a_ids == w_ids).all() and np.array_equal(a_sc, w_sc)
+    b_ids, _, _ = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
+    recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(w_ids, b_ids)])
+    assert recall >= 0.97, recall
