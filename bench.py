@@ -36,6 +36,10 @@ def parse_args():
     ap.add_argument("--m", type=int, default=16)
     ap.add_argument("--efc", type=int, default=200)
     ap.add_argument("--max-batch", type=int, default=8192, help="insertion batch of the GPU HNSW build")
+    ap.add_argument("--data", default="latent", choices=["latent", "gauss", "clustered"],
+                    help="synthetic embeddings: 'latent' (default, DESIGN.md 5) = 16-d gaussian latent -> linear map + 15 %% noise; 'gauss' = BASELINE.md 3's "
+                         "N(0,1) normalised; 'clustered' = BASELINE.md 3's 4 096 centres, points = normalise(centre + 0.1 * unit noise) (segment.rs:697-706)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (BASELINE configs 1 and 4 + the quantised walk at N = 1)")
     ap.add_argument("--latent", type=int, default=16)
     ap.add_argument("--noise", type=float, default=0.15)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the cpu_baseline sample")
@@ -67,6 +71,51 @@ def gen_vectors(n, d, device, seed, latent, noise, chunk=500_000):
         v /= v.norm(dim=1, keepdim=True)
         out[i:i + m] = v
     return out
+
+
+def gen_vectors_gauss(n, d, device, seed, chunk=500_000):
+    """BASELINE.md 3 / SURVEY 8d: standard normal f32, L2-normalised (isotropic: no neighbourhood structure at d = 768)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, d), device=device, dtype=torch.float32)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        v = torch.randn((m, d), generator=g, device=device, dtype=torch.float32)
+        v /= v.norm(dim=1, keepdim=True)
+        out[i:i + m] = v
+    return out
+
+
+def gen_vectors_clustered(n, d, device, seed, centres=4096, sigma=0.1, chunk=500_000):
+    """BASELINE.md 3's clustered variant: 4 096 random unit centres; a point = normalise(centre + sigma * unit fuzz), the
+    reference's random_nearby_vector (segment.rs:697-706, fuzz = U(-1, 1)^d normalised)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(4096)
+    c = torch.rand((centres, d), generator=g, device=device, dtype=torch.float32) * 2 - 1
+    c /= c.norm(dim=1, keepdim=True)
+    g.manual_seed(seed)
+    out = torch.empty((n, d), device=device, dtype=torch.float32)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        which = torch.randint(0, centres, (m,), generator=g, device=device)
+        fuzz = torch.rand((m, d), generator=g, device=device, dtype=torch.float32) * 2 - 1
+        fuzz /= fuzz.norm(dim=1, keepdim=True)
+        v = c[which] + sigma * fuzz
+        v /= v.norm(dim=1, keepdim=True)
+        out[i:i + m] = v
+    return out
+
+
+def make_vectors(args, n, d, device, seed):
+    if args.data == "gauss":
+        return gen_vectors_gauss(n, d, device, seed)
+    if args.data == "clustered":
+        return gen_vectors_clustered(n, d, device, seed)
+    return gen_vectors(n, d, device, seed=seed, latent=args.latent, noise=args.noise)
 
 
 def gen_queries(vecs, nq, seed, distance=0.05):
@@ -245,7 +294,7 @@ def main():
 
     # ---- setup (untimed): data, segment, GPU HNSW build, ground truth -------------------------------
     t0 = time.perf_counter()
-    vecs = gen_vectors(n, d, dev, seed=1234567890 + rank, latent=args.latent, noise=args.noise)
+    vecs = make_vectors(args, n, d, dev, seed=1234567890 + rank)
     n_batches = args.steps + args.warmup
     queries = [gen_queries(vecs, nq, seed=123 + i) for i in range(n_batches)]  # same on every rank for a given i? no: per-rank data
     if multi:  # every rank must search the SAME queries: take rank 0's
@@ -536,6 +585,19 @@ def main():
         hq0 = torch.cat(queries[args.warmup:]).cpu().numpy()   # the timed batches, in order
         cpu = run_cpu_baseline(O, host_vecs, og, hq0, ids_np, nq, k, ef, cores, args.cpu_seconds)
 
+    # ---- the other BASELINE configs, N = 1 only: exact scan (configs[0]), BM25 (configs[3]), the quantised walk ----
+    extra = None
+    if rank == 0 and not multi and not args.no_extra:
+        try:
+            import bench_extra as BX
+
+            seg.close()                      # 33 GB of vectors + graph back to the allocator first
+            del seg
+            torch.cuda.empty_cache()
+            extra = BX.driver_extras(steps=max(3, min(args.steps, 10)), warmup=max(3, min(args.warmup, 5)))
+        except Exception as e:  # noqa: BLE001  (the headline line must survive a failure of the side measurements)
+            extra = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         qps_units = world * nq * args.steps / (ms_total * 1e-3)
         line = {
@@ -544,7 +606,9 @@ def main():
             "config": {"workload": workload, "segments": world, "vectors_per_segment": n, "exchange": ("pipelined, 2 batches in flight (torch)" if pipelined else ("in line, nidx_vec_search_sharded (ncclAllGather + Fssc merge in the library)" if use_lib else "in line, torch all_gather + nidx_merge_topk")) if multi else None,
                        "M": m, "M0": m0, "efC": args.efc, "l2": f"inputs larger than L2 ({n * d * 4 / 1e9:.1f} GB of vectors per GPU, fresh queries every step)",
                        "unit_note": "one unit = one query searched on one segment; merged_qps = user-visible queries/s over all segments",
-                       "data_gen": f"latent={args.latent} noise={args.noise} normalised; queries = data point + 0.05 * unit noise"},
+                       "data_gen": ({"latent": f"latent={args.latent} noise={args.noise} normalised", "gauss": "N(0,1) normalised (BASELINE.md 3)",
+                                     "clustered": "4096 centres, normalise(centre + 0.1 * unit fuzz) (BASELINE.md 3)"}[args.data]
+                                    + "; queries = data point + 0.05 * unit noise")},
             "merged_qps": nq * args.steps / (ms_total * 1e-3),
             "exchange_in_line_ms_per_step": inline_ms,
             "recall_at_10": recall,
@@ -557,6 +621,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * (12 if use_lib else 8) + nq * 4, **e2e_mode},
             "gpu_launches": int(launches),
+            "extra": extra,
             "visited_overflows": int(overflow),
             "clocks": clocks.summary(),
         }

@@ -234,6 +234,7 @@ def bench_bm25(args):
         out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
                torch.empty((nq,), dtype=torch.int32, device=dev), torch.empty((nq,), dtype=torch.int64, device=dev))
         ms = timed(lambda: ts.search(qt, qoff, k, mode=mode, use_tf=use_tf, out=out), args.steps, args.warmup)
+        kms = ts.last_kernel_ms()
         postings = sum(int(df[t]) for q in queries for t in q)
         alg = postings * ((8 if use_tf else 4) + 1)
         # host path (e2e): numpy in / numpy out through the C ABI
@@ -253,21 +254,101 @@ def bench_bm25(args):
         rel = float(np.max(np.abs(sc[:ns] - osc) / np.maximum(1.0, np.abs(osc))))
         same_ids = float(np.mean(docs[:ns] == od))
         pk = float(peaks().get("hbm_gbs", 6650.0))
-        ach = alg / (ms * 1e-3) / 1e9
+        ach = alg / (kms * 1e-3) / 1e9
         lines.append({"metric": "BM25 QPS", "value": nq / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": ms, "higher_is_better": True, "dtype": "f32 (u32 fixed-point accumulate)", "data": "synthetic",
                       "config": {"workload": f"BM25 {n_docs} docs / {nterms}-term queries, top-{k}, {name}", "vocab": n_terms, "postings": int(c['term_off'][-1]),
                                  "postings_per_query": postings / nq, "setup_seconds": t_setup},
                       "parity": {"counts_identical_to_oracle": ok_counts, "max_rel_score_diff": rel, "ids_identical_fraction": same_ids, "sample": ns},
-                      "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "bm25_kernel", "kernel_ms": ms, "traffic": None},
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "bm25_kernel", "kernel_ms": kms, "traffic": None,
+                                   "alg_bytes_note": "postings x (8 with tf, 4 + 1 for tf == 1: SURVEY 8d); the records read are 8 B either way"},
                       "cpu_baseline": {"value": ns / cpu_dt, "unit": "queries/s", "cores": effective_cores(), "kind": "port", "sample": f"{ns} queries"},
                       "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(qt_h.nbytes + qo_h.nbytes), "d2h_bytes_per_step": nq * k * 8 + nq * 12}})
     return lines
 
 
+def bench_rabitq(args):
+    """the HNSW walk with a RaBitQ query on a Dot index (hnsw/search.rs:306-383: estimate-ranked walk, k * 100
+    layer-0 results, exact rerank) -- what the reference runs on every Dot index that carries vectors.quant -- next to the dense
+    walk on the same graph.  Algorithmic bytes per query = estimates x code bytes + expansions x adjacency row + exact
+    similarities x row bytes, from the kernel's counters."""
+    import torch
+
+    from bench import gen_queries, gen_vectors, recall_at_k
+    from nucliadb_b200 import _lib
+    from nucliadb_b200.segment import VectorSegment
+
+    dev = torch.device("cuda", 0)
+    n, d, nq, k = args.build_vectors, 768, 1024, 10
+    vecs = gen_vectors(n, d, dev, seed=1234567890, latent=16, noise=0.15)
+    queries = [gen_queries(vecs, nq, seed=123 + i) for i in range(args.steps + args.warmup)]
+    seg = VectorSegment.create(vecs, d, similarity=_lib.NIDX_SIM_DOT, m=16, m0=32, ef_construction=200)
+    del vecs
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    seg.build_hnsw(seed=2, max_batch=8192)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    seg.rabitq_encode()
+    gt = seg.search(queries[0], k, method=_lib.NIDX_METHOD_BRUTE)[0].cpu().numpy()
+    out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq,), dtype=torch.int32, device=dev))
+    lines = []
+    pk = float(peaks().get("hbm_gbs", 6650.0))
+    for name, method, ef in (("quantised walk (RaBitQ query, 1000 layer-0 candidates, exact rerank)", _lib.NIDX_METHOD_HNSW_RABITQ, 0),
+                             ("dense walk ef=128", _lib.NIDX_METHOD_HNSW, 128)):
+        idx = [0]
+
+        def step():
+            seg.search(queries[idx[0] % len(queries)], k, ef=ef, method=method, out=out)
+            idx[0] += 1
+
+        ms = timed(step, args.steps, args.warmup)
+        seg.search(queries[0], k, ef=ef, method=method, out=out)
+        kms = seg.last_kernel_ms()
+        c = seg.counters_ex()
+        rec = recall_at_k(out[0].cpu().numpy(), gt)
+        stride = (d // 8 + 8 + 15) // 16 * 16
+        alg = c["estimates"] * stride + c["expansions"] * 32 * 4 + c["similarities"] * (d * 4 + 4)
+        lines.append({"metric": "k-NN QPS @ recall@10", "value": nq / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms, "higher_is_better": True, "dtype": "f32 + 1-bit codes" if method == _lib.NIDX_METHOD_HNSW_RABITQ else "f32", "data": "synthetic",
+                      "config": {"workload": f"HNSW search {n}x{d} dot, {name}, k={k}, batch={nq}", "M": 16, "M0": 32, "efC": 200, "build_seconds": t_build},
+                      "recall_at_10": rec, "counters_per_query": {kk: v / nq for kk, v in c.items()},
+                      "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": pk, "unit": "GB/s", "frac": alg / (kms * 1e-3) / 1e9 / pk,
+                                   "kernel": "hnsw_rabitq_kernel" if method == _lib.NIDX_METHOD_HNSW_RABITQ else "hnsw_search_kernel", "kernel_ms": kms,
+                                   "alg_bytes_per_query": alg / nq, "traffic": None,
+                                   "note": "latency bound: ~1000 dependent expansions per query, 1024 queries in flight" if method == _lib.NIDX_METHOD_HNSW_RABITQ else None}})
+    seg.close()
+    return lines
+
+
+def driver_extras(steps=5, warmup=3):
+    """The `extra` block of bench.py's line (N = 1): BASELINE configs[0] (exact scan), configs[3] (BM25) and the quantised walk on a
+    1 M x 768 Dot index, each reduced to the keys a reader needs; the full lines are what `bench_extra.py` prints."""
+    import torch
+
+    class A:
+        pass
+
+    a = A()
+    a.steps, a.warmup, a.docs, a.build_vectors = steps, warmup, 5_000_000, 1_000_000
+
+    def compact(line):
+        keep = ("metric", "value", "unit", "ms_per_step", "config", "parity", "recall_at_10", "roofline", "cpu_baseline", "e2e", "counters_per_query")
+        return {kk: line[kk] for kk in keep if kk in line}
+
+    out = {}
+    for name, fn in (("scan", bench_scan), ("bm25", bench_bm25), ("rabitq_walk", bench_rabitq)):
+        try:
+            out[name] = [compact(x) for x in fn(a)]
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["scan", "bm25", "build", "merge", "all"])
+    ap.add_argument("which", choices=["scan", "bm25", "build", "merge", "rabitq", "all"])
     ap.add_argument("--build-vectors", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -282,6 +363,8 @@ def main():
         lines += bench_build(args)
     if args.which == "merge":
         lines += bench_merge(args)
+    if args.which == "rabitq":
+        lines += bench_rabitq(args)
     for line in lines:
         print(json.dumps(line))
 

@@ -22,6 +22,7 @@
 #include "rabitq.cuh"
 #include "scan.cu"
 #include "scan_tc.cuh"
+#include "scan_tc2.cuh"
 #include "segment_io.hpp"
 #include "shard.cuh"
 #include "topk.cuh"
@@ -136,6 +137,10 @@ struct nidx_vec_segment {
     uint32_t* d_adj0 = nullptr; float* d_w0 = nullptr;
     uint64_t* d_upper_off = nullptr;
     uint32_t* d_adjU = nullptr; float* d_wU = nullptr;
+    float max_norm = 0.0f;              // max |v| (error bound of the tensor-core filter for Dot)
+    CUtensorMap map_v;                  // TMA descriptor of the vector block (scan_tc2.cuh), built on first use
+    bool map_v_ready = false;
+    std::mutex map_mu;
     unsigned char* d_quant = nullptr;   // RaBitQ codes [n][quant_stride] (vectors.quant records, padded)
     int quant_stride = 0;
     unsigned long long* d_counters = nullptr;  // [4]
@@ -195,6 +200,36 @@ static int alloc_graph(nidx_vec_segment* s, const uint8_t* level) {
     CU(cudaMemset(s->d_w0, 0, n0 * 4));
     CU(cudaMemset(s->d_adjU, 0xFF, nu * 4));
     CU(cudaMemset(s->d_wU, 0, nu * 4));
+    return 0;
+}
+
+__global__ void max_norm_kernel(const float* __restrict__ norms, uint64_t n, unsigned int* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = fmaxf(m, norms[i]);
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order like their bit patterns
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_row_tensor_map(CUtensorMap* map, const float* base, uint64_t rows, int ld, int box_rows) {
+    static tmap_encode_fn encode = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<tmap_encode_fn>(fn);
+    });
+    if (!encode) return fail(NIDX_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC2_KB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NIDX_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
 
@@ -259,6 +294,17 @@ static int finish_create(nidx_vec_segment* s, const uint32_t* paragraph_of_host)
             CU(cudaMalloc(&s->d_par_first, first.size() * 4));
             CU(cudaMemcpy(s->d_par_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
         }
+    }
+    if (n) {   // max |v| for the Dot error bound of the tensor-core filter
+        unsigned int* d_bits = nullptr;
+        CU(cudaMalloc(&d_bits, 4));
+        CU(cudaMemset(d_bits, 0, 4));
+        max_norm_kernel<<<std::min<uint64_t>((n + 255) / 256, (uint64_t)s->sm_count * 8), 256>>>(s->d_norms, n, d_bits);
+        LAUNCHED();
+        unsigned int hb = 0;
+        CU(cudaMemcpy(&hb, d_bits, 4, cudaMemcpyDeviceToHost));
+        cudaFree(d_bits);
+        memcpy(&s->max_norm, &hb, 4);
     }
     CU(cudaMalloc(&s->d_counters, 8 * sizeof(unsigned long long)));
     CU(cudaMemset(s->d_counters, 0, 8 * sizeof(unsigned long long)));
@@ -599,6 +645,16 @@ static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list
 
 }  // extern "C"
 
+// The tensor-core filter + refine path serves large batches of small-k queries on single-vector segments whose rows are whole
+// 128-byte swizzle rows.  NIDX_B200_SCAN=exact forces the CUDA-core kernels (same results, bit for bit), =tensor forces the filter.
+static bool use_tc_filter(const nidx_vec_segment* s, int nq, int k) {
+    if (k > TC2_KMAX || s->ld % TC2_KB != 0 || s->d_par_first || s->n < (uint64_t)TC2_N) return false;
+    const char* e = getenv("NIDX_B200_SCAN");
+    if (e && !strcmp(e, "exact")) return false;
+    if (e && !strcmp(e, "tensor")) return true;
+    return nq >= 64;
+}
+
 // The body of nidx_vec_search.  qhost: the queries (and filter bits) are host pointers; ohost: the outputs are host pointers
 // (copied back and the stream synchronised before returning).  The sharded entry point (shard.cuh) passes host queries with
 // device outputs: the partial results go straight into the exchange buffer.
@@ -718,6 +774,41 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         CU(cudaMemsetAsync(d_ids, 0xFF, (size_t)nq * k * 4, stream));
         CU(cudaMemsetAsync(d_sc, 0, (size_t)nq * k * 4, stream));
         CU(cudaMemsetAsync(d_cnt, 0, (size_t)nq * 4, stream));
+    } else if (method == NIDX_METHOD_BRUTE && use_tc_filter(s, nq, k)) {
+        // large batch: TF32 tensor-core filter + bit-exact refine (scan_tc2.cuh); nothing of size [Q x N] touches HBM
+        int n_chunks = (int)((s->n + TC2_CHUNK - 1) / TC2_CHUNK), n_qblocks = (nq + TC2_M - 1) / TC2_M;
+        {
+            std::lock_guard<std::mutex> lk(s->map_mu);
+            if (!s->map_v_ready) {
+                int mr = make_row_tensor_map(&s->map_v, s->d_vecs, s->n, s->ld, TC2_N);
+                if (mr) return mr;
+                s->map_v_ready = true;
+            }
+        }
+        CUtensorMap map_q;
+        int mr = make_row_tensor_map(&map_q, dq, (uint64_t)nq, s->ld, TC2_M);
+        if (mr) return mr;
+        size_t cand_n = (size_t)nq * n_chunks * TC2_L;
+        ENSURE(w.scores, cand_n * 8 + 64);
+        ENSURE(w.sched, 64);
+        Tc2Args ta;
+        ta.nq = nq; ta.n_qblocks = n_qblocks; ta.n_chunks = n_chunks; ta.qnorms = w.qnorms.as<float>(); ta.bits = bits;
+        ta.cand_score = w.scores.as<float>(); ta.cand_id = reinterpret_cast<uint32_t*>(w.scores.as<float>() + cand_n);
+        ta.work_counter = w.sched.as<unsigned int>();
+        CU(cudaFuncSetAttribute(scan_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
+        int grid = std::min(n_chunks * n_qblocks, s->sm_count);
+        CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        CU(cudaEventRecord(s->ev_k0, stream));
+        scan_tc_filter_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, stream>>>(map_q, s->map_v, V, ta);
+        CU(cudaEventRecord(s->ev_k1, stream));
+        LAUNCHED();
+        int cap = topk_cap(k, 256);
+        size_t smem_rf = tc2_refine_smem(s->ld, cap);
+        if (smem_rf > 48 * 1024) CU(cudaFuncSetAttribute(scan_tc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rf));
+        scan_tc_refine_kernel<<<nq, 256, smem_rf, stream>>>(V, dq, w.qnorms.as<float>(), n_chunks, ta.cand_score, ta.cand_id, bits, s->max_norm, p->min_score, k, cap,
+                                                            d_ids, d_sc, d_cnt, s->d_counters + 6);
+        LAUNCHED();
+        CU(cudaGetLastError());
     } else if (method == NIDX_METHOD_BRUTE) {
         if (k > 1024) return fail(NIDX_EINVAL, "brute-force k above 1024 not supported");
         int cap = topk_cap(k, 256);
@@ -735,7 +826,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         // Batches of >= 128 queries go to the tensor cores (scores within ~3e-7 of the lane-blocked order);
         // NIDX_B200_SCAN=exact forces the bit-exact CUDA-core kernel, =tensor forces the tensor path.
         const char* scan_env = getenv("NIDX_B200_SCAN");
-        bool tensor_scan = s->ld % TC_KB == 0 && ((nq >= 128 && !(scan_env && !strcmp(scan_env, "exact"))) || (scan_env && !strcmp(scan_env, "tensor")));
+        bool tensor_scan = s->ld % TC_KB == 0 && scan_env && !strcmp(scan_env, "tensor3x");   // round 1's 3xTF32 score-matrix kernel: on request only
         if (tensor_scan) CU(cudaFuncSetAttribute(scan_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         if (smem_scan > 48 * 1024) CU(cudaFuncSetAttribute(scan_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         if ((size_t)cap * 8 > 48 * 1024) {
@@ -1434,10 +1525,7 @@ static int txt_search_impl(nidx_txt_segment* t, const uint32_t* query_terms, con
 
     bool conj = p->mode == NIDX_BM25_AND;
     int cap = topk_cap(k, BM_THREADS);
-    // accumulator table: 8192 slots (two CTAs per SM); NIDX_B200_BM25_BITS overrides (13..15) for experiments
-    int hash_bits = 13;
-    if (const char* e = getenv("NIDX_B200_BM25_BITS")) { int b = atoi(e); if (b >= 13 && b <= 15) hash_bits = b; }
-    size_t smem = bm_smem_bytes(cap, hash_bits, conj);
+    size_t smem = bm_smem_bytes(cap, conj);
     if (smem > 220 * 1024) return fail(NIDX_EINVAL, "BM25 needs %zu bytes of shared memory (k=%d): too large", smem, k);
     ENSURE(w.partial, (size_t)nq * k * 8);
     ENSURE(w.misc, (size_t)nq * 8);
@@ -1454,7 +1542,7 @@ static int txt_search_impl(nidx_txt_segment* t, const uint32_t* query_terms, con
     T.n_docs = t->n_docs; T.n_terms = t->n_terms; T.n_fine = t->n_fine; T.term_off = t->d_term_off; T.post = t->d_post;
     T.skip_row = t->d_skip_row; T.skip = t->d_skip; T.alive = t->d_alive;
     Bm25Args a;
-    a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.k = k; a.cap = cap; a.hash_bits = hash_bits;
+    a.query_terms = d_qt; a.query_off = d_qo; a.nq = nq; a.k = k; a.cap = cap;
     a.term_weight = t->d_weight; a.norm_cache = t->d_norm_cache; a.shift = shift;
     a.after_mode = p->after_mode; a.after_score = p->after_score; a.after_docaddr = p->after_docaddr; a.docaddr_base = p->docaddr_base;
     a.out_keys = w.partial.as<uint64_t>(); a.out_total = d_total; a.error_flag = t->d_error;

@@ -100,43 +100,55 @@ def test_stored_paragraph_bytes_and_store_round_trip(tmp_path):
         PS.read_paragraphs(str(tmp_path))
 
 
-# ---- the chunk map of bm25_kernel (csrc/bm25.cuh resolve()), restated in Python --------------------------------------------------
-def test_bm25_chunk_map_covers_every_posting_once():
-    """resolve(): run r of a tile has ceil(len_r / 32) chunks; pre[] is the exclusive prefix of the chunk counts in TERM order
-    (the warp scans lanes, then carries over the 32-term groups), chunk_run[g] names the run of chunk g.  In pass 1 warp w takes
-    chunks w, w + 8, ... four at a time; lane l of chunk g handles posting (g - pre[r]) * 32 + l of run r.  Every posting of the
-    tile must be visited exactly once."""
+# ---- the octet map of bm25_kernel (csrc/bm25.cuh resolve() / load_round()), restated in Python ------------------------------------
+def test_bm25_octet_map_covers_every_posting_once():
+    """resolve(): run r of a tile has ceil(len_r / 8) octets; pre8[] is the exclusive prefix of the octet counts in TERM order
+    (the warp scans lanes, then carries over the 32-term groups), omap[o] names the run of octet o.  load_round(): thread t owns
+    slots round * 4096 + u * 256 + t (u < 16); slot s is posting (s >> 3 - pre8[r]) * 8 + (s & 7) of run r = omap[s >> 3] (one
+    round) or of the last run with pre8[r] <= s >> 3 (several rounds).  Every posting of the tile must be visited exactly once."""
     rng = np.random.default_rng(12)
-    warps, unroll = 8, 4
-    for trial in range(60):
+    threads, pt = 256, 16
+    slots = threads * pt
+    for trial in range(40):
         nt = int(rng.integers(1, 129))
-        lens = (rng.integers(0, 200, nt) * (rng.random(nt) < 0.7)).astype(np.int64)
+        scale = 40 if trial % 3 else 700                  # every third trial needs several rounds
+        lens = (rng.integers(0, scale, nt) * (rng.random(nt) < 0.7)).astype(np.int64)
         if trial == 0:
             lens[:] = 0
-        chunks = (lens + 31) >> 5
+        octs = (lens + 7) >> 3
         pre = np.zeros(nt + 1, dtype=np.int64)
         run = 0
         for j in range(0, nt, 32):                       # the kernel's order: 32 terms per shuffle scan, carry `run`
-            c = chunks[j:j + 32]
+            c = octs[j:j + 32]
             pre[j:j + len(c)] = run + np.cumsum(c) - c
             run += int(c.sum())
         pre[nt] = run
-        chunk_run = np.full(max(run, 1), -1)
+        noct = run
+        one_round = noct <= slots // 8
+        omap = np.full(max(noct, 1), -1)
         for r in range(nt):
-            chunk_run[pre[r]:pre[r] + chunks[r]] = r
+            omap[pre[r]:pre[r] + octs[r]] = r
         seen = [np.zeros(n, dtype=np.int64) for n in lens]
-        for w in range(warps):
-            for g0 in range(w, run, warps * unroll):
-                for u in range(unroll):
-                    g = g0 + u * warps
-                    if g >= run:
-                        continue
-                    r = chunk_run[g]
-                    assert r >= 0
-                    for lane in range(32):
-                        within = (g - pre[r]) * 32 + lane
-                        if within < lens[r]:
-                            seen[r][within] += 1
+        for rnd in range(-(-noct // (slots // 8))):
+            for s in range(rnd * slots, (rnd + 1) * slots):
+                o = s >> 3
+                if o >= noct:
+                    continue
+                if one_round:
+                    r = omap[o]
+                else:
+                    lo, hi = 0, nt - 1
+                    while lo < hi:
+                        mid = (lo + hi + 1) >> 1
+                        if pre[mid] <= o:
+                            lo = mid
+                        else:
+                            hi = mid - 1
+                    r = lo
+                    assert r == omap[o]
+                within = (o - pre[r]) * 8 + (s & 7)
+                if within < lens[r]:
+                    seen[r][within] += 1
         assert all((x == 1).all() for x in seen)
 
 
