@@ -40,6 +40,8 @@ extern "C" {
 
 #define NIDX_SIM_DOT 0     /* config.rs:33-37 Similarity::Dot */
 #define NIDX_SIM_COSINE 1  /* Similarity::Cosine */
+#define NIDX_SIM_L2 2      /* extension (north_star): -|a - b|^2 as a similarity; the reference has no L2 (config.rs:33-37), so parity is
+                              against the oracle's restatement and a float64 brute force only */
 
 #define NIDX_METHOD_AUTO 0   /* segment.rs:538 use_hnsw() cost model decides */
 #define NIDX_METHOD_HNSW 1   /* hnsw/search.rs:306-383 */
@@ -149,6 +151,39 @@ typedef struct nidx_vec_search_params {
  * out_counts[nq] the number of valid results per query. */
 int nidx_vec_search(nidx_vec_segment* seg, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p,
                     uint32_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Filters on the device (reference: ParagraphInvertedIndexes, inverted_index/paragraph.rs:39-186 over fst_index.rs + map.rs)
+ * ------------------------------------------------------------------------------------------ */
+#define NIDX_INV_LABELS 0  /* label index: key = labels_key(label) (paragraph.rs:64-66), looked up by PREFIX (get_prefix) */
+#define NIDX_INV_FIELDS 1  /* field index: key = FieldKey bytes (utils.rs:80-117), looked up EXACTLY (get) */
+/* One inverted index of the segment: n_keys byte strings, strictly ascending in memcmp order (the fst's order), key i =
+ * key_bytes[key_off[i] .. key_off[i + 1]), its paragraph addresses = postings[post_off[i] .. post_off[i + 1]).  The keys stay on the
+ * host side of the library (the lookup is the fst's job: a binary search), the postings live in HBM.  Host pointers. */
+int nidx_vec_set_inverted_index(nidx_vec_segment* seg, int32_t which, uint32_t n_keys, const uint8_t* key_bytes, const uint64_t* key_off,
+                                const uint64_t* post_off, const uint32_t* postings);
+
+#define NIDX_F_LABEL 0  /* AtomClause::Label: n = 1 key, every label key that starts with it (formula.rs:21, paragraph.rs:140-142) */
+#define NIDX_F_KEYS 1   /* AtomClause::KeyPrefixSet: n field keys, each looked up exactly (paragraph.rs:143-147) */
+#define NIDX_F_AND 2    /* CompoundClause And: intersection of the n operand nodes that follow */
+#define NIDX_F_OR 3     /* CompoundClause Or: union */
+#define NIDX_F_NOT 4    /* CompoundClause Not: complement of the INTERSECTION of its n operands (paragraph.rs:160-178) */
+typedef struct nidx_filter_node {   /* a Formula / Clause tree in pre-order (formula.rs:40-100); a Formula with several clauses is an AND / OR root */
+    int32_t kind;                   /* NIDX_F_* */
+    int32_t n;                      /* LABEL: 1; KEYS: number of keys; AND / OR / NOT: number of operand subtrees that follow */
+    const uint8_t* const* keys;     /* LABEL / KEYS: n byte strings (host pointers) */
+    const uint32_t* key_len;
+} nidx_filter_node;
+
+/* ParagraphInvertedIndexes::filter + the intersection with the alive set (segment.rs:516-531): the formula's bitset over the
+ * paragraphs, computed in HBM (postings -> bits, bit algebra, popcount).  out_bits (`mem`; (paragraphs + 63) / 64 words) may be NULL;
+ * *out_matching = number of set bits (the reference's `bitset.iter().count()`). */
+int nidx_vec_filter(nidx_vec_segment* seg, const nidx_filter_node* nodes, int32_t n_nodes, uint64_t* out_bits, int mem, uint64_t* out_matching, void* stream);
+
+/* nidx_vec_search with the filter given as a formula: evaluated on the device and fed to the search without a host round trip
+ * (p->filter_bits must be NULL; NIDX_METHOD_AUTO reads the match count back, 8 bytes, for the cost model as segment.rs:531 does). */
+int nidx_vec_search_formula(nidx_vec_segment* seg, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p,
+                            const nidx_filter_node* nodes, int32_t n_nodes, uint32_t* out_ids, float* out_scores, int32_t* out_counts, void* stream);
 
 /* Searcher::_search's cross-segment / cross-shard top-k (searcher.rs:241-290 Fssc without the string
  * keys, shard_merge.rs:332-348): merge n_parts partial results [n_parts][nq][k] (score desc) into

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnidx_b200.so")
 
 NIDX_MEM_HOST, NIDX_MEM_DEVICE = 0, 1
-NIDX_SIM_DOT, NIDX_SIM_COSINE = 0, 1
+NIDX_SIM_DOT, NIDX_SIM_COSINE, NIDX_SIM_L2 = 0, 1, 2
 NIDX_METHOD_AUTO, NIDX_METHOD_HNSW, NIDX_METHOD_BRUTE, NIDX_METHOD_BRUTE_RABITQ, NIDX_METHOD_HNSW_RABITQ = 0, 1, 2, 3, 4
 NIDX_BM25_OR, NIDX_BM25_AND = 0, 1
 NIL = 0xFFFFFFFF
@@ -22,6 +22,7 @@ SYMBOLS = [
     "nidx_last_error", "nidx_device_count", "nidx_launch_count",
     "nidx_vec_create", "nidx_vec_open", "nidx_vec_save", "nidx_vec_close", "nidx_vec_len", "nidx_vec_device_vectors",
     "nidx_use_hnsw", "nidx_hnsw_levels", "nidx_vec_build_hnsw", "nidx_vec_extend_hnsw", "nidx_vec_graph_dims", "nidx_vec_set_graph", "nidx_vec_get_graph", "nidx_vec_set_alive",
+    "nidx_vec_set_inverted_index", "nidx_vec_filter", "nidx_vec_search_formula",
     "nidx_vec_search", "nidx_merge_topk", "nidx_vec_counters", "nidx_vec_counters_ex", "nidx_vec_last_kernel_ms",
     "nidx_vec_rabitq_encode", "nidx_vec_rabitq_codes", "nidx_vec_rabitq_estimate",
     "nidx_txt_create", "nidx_txt_set_stats", "nidx_txt_set_alive", "nidx_txt_close", "nidx_txt_search", "nidx_txt_last_kernel_ms",
@@ -45,6 +46,14 @@ class VecConfig(C.Structure):
 class VecSearchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("ef", C.c_int32), ("min_score", C.c_float), ("with_duplicates", C.c_int32), ("method", C.c_int32),
                 ("filter_bits", C.c_void_p), ("filter_matching", C.c_uint64)]
+
+
+class FilterNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("keys", C.POINTER(C.c_void_p)), ("key_len", C.POINTER(C.c_uint32))]   # keys are raw bytes (may hold NULs)
+
+
+NIDX_INV_LABELS, NIDX_INV_FIELDS = 0, 1
+NIDX_F_LABEL, NIDX_F_KEYS, NIDX_F_AND, NIDX_F_OR, NIDX_F_NOT = 0, 1, 2, 3, 4
 
 
 class TxtSearchParams(C.Structure):

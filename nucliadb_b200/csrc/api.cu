@@ -126,7 +126,14 @@ struct nidx_vec_segment {
     uint32_t* d_par_first = nullptr;
     uint32_t n_par = 0;
     uint64_t* d_alive = nullptr;
+    uint64_t alive_count = 0;         // set bits of d_alive (counted in nidx_vec_set_alive): `matching` of an unfiltered search
     uint64_t* d_par_keys = nullptr;   // [n_par] caller-supplied paragraph keys for the cross-segment de-duplication (shard.cuh)
+    struct InvIndex {                 // one inverted index (inverted_index/fst_index.rs + map.rs): sorted keys on the host, postings in HBM
+        std::vector<unsigned char> key_bytes;
+        std::vector<uint64_t> key_off, post_off;
+        uint32_t* d_post = nullptr;
+        uint32_t n_keys = 0;
+    } inv[2];
     // graph
     bool has_graph = false;
     std::vector<uint8_t> h_level;
@@ -253,7 +260,7 @@ static int check_device(int device) {
 
 static int fill_defaults(nidx_vec_config* c) {
     if (c->dimension <= 0) return fail(NIDX_EINVAL, "dimension must be positive");
-    if (c->similarity != NIDX_SIM_DOT && c->similarity != NIDX_SIM_COSINE) return fail(NIDX_EINVAL, "unknown similarity %d", c->similarity);
+    if (c->similarity != NIDX_SIM_DOT && c->similarity != NIDX_SIM_COSINE && c->similarity != NIDX_SIM_L2) return fail(NIDX_EINVAL, "unknown similarity %d", c->similarity);
     if (c->m <= 0) c->m = 30;                              // params.rs:40
     if (c->m0 <= 0) c->m0 = 60;                            // params.rs:34
     if (c->ef_construction <= 0) c->ef_construction = 100; // params.rs:43
@@ -376,7 +383,7 @@ void nidx_vec_close(nidx_vec_segment* s) {
     cudaDeviceSynchronize();
     free_graph(s);
     cudaFree(s->d_vecs); cudaFree(s->d_norms); cudaFree(s->d_par_of); cudaFree(s->d_par_first); cudaFree(s->d_alive);
-    cudaFree(s->d_counters); cudaFree(s->d_work_counter); cudaFree(s->d_quant); cudaFree(s->d_par_keys);
+    cudaFree(s->d_counters); cudaFree(s->d_work_counter); cudaFree(s->d_quant); cudaFree(s->d_par_keys); cudaFree(s->inv[0].d_post); cudaFree(s->inv[1].d_post);
     if (s->ev_k0) cudaEventDestroy(s->ev_k0);
     if (s->ev_k1) cudaEventDestroy(s->ev_k1);
     delete s;
@@ -394,8 +401,18 @@ int nidx_vec_set_alive(nidx_vec_segment* s, const uint64_t* alive_bits, int mem)
     CU(cudaSetDevice(s->cfg.device));
     if (!alive_bits) { cudaFree(s->d_alive); s->d_alive = nullptr; return 0; }
     size_t words = ((size_t)s->n_par + 63) / 64;
-    if (!s->d_alive) CU(cudaMalloc(&s->d_alive, std::max<size_t>(words, 1) * 8));
+    if (!s->d_alive) CU(cudaMalloc(&s->d_alive, std::max<size_t>(words, 1) * 8 + 8));
     CU(cudaMemcpy(s->d_alive, alive_bits, words * 8, mem == NIDX_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    // the number of alive paragraphs: what the reference counts per request (segment.rs:531) when there is no filter
+    std::vector<uint64_t> h(words);
+    if (words) CU(cudaMemcpy(h.data(), s->d_alive, words * 8, cudaMemcpyDeviceToHost));
+    uint64_t cnt = 0;
+    for (size_t i = 0; i < words; ++i) {
+        uint64_t v = h[i];
+        if ((i + 1) * 64 > s->n_par) v &= s->n_par > i * 64 ? (~0ull >> (64 - (s->n_par - i * 64))) : 0ull;
+        cnt += (uint64_t)__builtin_popcountll(v);
+    }
+    s->alive_count = cnt;
     return 0;
 }
 
@@ -645,10 +662,152 @@ static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list
 
 }  // extern "C"
 
+// ---- filter formulas on the device (inverted_index/paragraph.rs:124-186) ---------------------------------------------
+// ranges[2r], ranges[2r + 1] = [begin, end) into the postings of one inverted index; one block per range sets the bits
+__global__ void bits_scatter_kernel(const uint32_t* __restrict__ postings, const uint64_t* __restrict__ ranges, uint64_t* __restrict__ out) {
+    uint64_t b = ranges[2 * blockIdx.x], e = ranges[2 * blockIdx.x + 1];
+    for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        uint32_t p = postings[i];
+        atomicOr(reinterpret_cast<unsigned long long*>(out) + (p >> 6), 1ull << (p & 63));
+    }
+}
+// op 0: a &= b, 1: a |= b, 2: a = ~a (bits beyond n_bits stay clear)
+__global__ void bits_combine_kernel(uint64_t* __restrict__ a, const uint64_t* __restrict__ b, size_t words, uint64_t n_bits, int op) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t v = a[i];
+        if (op == 0) v &= b[i];
+        else if (op == 1) v |= b[i];
+        else {
+            v = ~v;
+            if ((i + 1) * 64 > n_bits) v &= n_bits > i * 64 ? (~0ull >> (64 - (n_bits - i * 64))) : 0ull;
+        }
+        a[i] = v;
+    }
+}
+
+struct FilterEval {
+    nidx_vec_segment* s;
+    const nidx_filter_node* nodes;
+    int n_nodes;
+    uint64_t* bufs;          // [n_nodes + 1][words] device
+    size_t words;
+    cudaStream_t stream;
+    std::vector<uint64_t> ranges;     // all atoms' ranges, uploaded once
+    std::vector<std::pair<size_t, size_t>> atom_ranges;   // per atom node: [first, count) in `ranges`
+    uint64_t* d_ranges = nullptr;
+    int next_buf = 0;
+
+    static int cmp_key(const unsigned char* a, size_t la, const unsigned char* b, size_t lb) {
+        int c = memcmp(a, b, std::min(la, lb));
+        return c ? c : (la < lb ? -1 : (la > lb ? 1 : 0));
+    }
+    // first key >= q
+    static uint32_t lower_bound(const nidx_vec_segment::InvIndex& ix, const unsigned char* q, size_t lq) {
+        uint32_t lo = 0, hi = ix.n_keys;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) / 2;
+            if (cmp_key(ix.key_bytes.data() + ix.key_off[mid], ix.key_off[mid + 1] - ix.key_off[mid], q, lq) < 0) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    }
+    // host pass: the key lookups (the fst's job in the reference), in node order
+    int collect(int i) {
+        const nidx_filter_node& nd = nodes[i];
+        if (nd.kind == NIDX_F_LABEL || nd.kind == NIDX_F_KEYS) {
+            const nidx_vec_segment::InvIndex& ix = s->inv[nd.kind == NIDX_F_LABEL ? NIDX_INV_LABELS : NIDX_INV_FIELDS];
+            size_t first = ranges.size() / 2;
+            for (int j = 0; j < nd.n; ++j) {
+                const unsigned char* q = nd.keys[j];
+                size_t lq = nd.key_len[j];
+                uint32_t lo = lower_bound(ix, q, lq), hi = lo;
+                if (nd.kind == NIDX_F_LABEL) {   // get_prefix: every key that starts with q
+                    uint32_t a = lo, b = ix.n_keys;
+                    while (a < b) {
+                        uint32_t mid = (a + b) / 2;
+                        size_t lk = ix.key_off[mid + 1] - ix.key_off[mid];
+                        bool starts = lk >= lq && memcmp(ix.key_bytes.data() + ix.key_off[mid], q, lq) == 0;
+                        if (starts) a = mid + 1; else b = mid;
+                    }
+                    hi = a;
+                } else if (lo < ix.n_keys && cmp_key(ix.key_bytes.data() + ix.key_off[lo], ix.key_off[lo + 1] - ix.key_off[lo], q, lq) == 0) {
+                    hi = lo + 1;                  // get: the exact key
+                }
+                if (hi > lo && ix.post_off[hi] > ix.post_off[lo]) { ranges.push_back(ix.post_off[lo]); ranges.push_back(ix.post_off[hi]); }
+            }
+            atom_ranges[i] = {first, ranges.size() / 2 - first};
+            return i + 1;
+        }
+        int j = i + 1;
+        for (int c = 0; c < nd.n; ++c) { if (j >= n_nodes) return -1; j = collect(j); if (j < 0) return -1; }
+        return j;
+    }
+    // device pass: returns the buffer holding node i's bitset, *next = the node after its subtree
+    uint64_t* eval(int i, int* next) {
+        const nidx_filter_node& nd = nodes[i];
+        uint64_t* out = bufs + (size_t)(next_buf++) * words;
+        if (nd.kind == NIDX_F_LABEL || nd.kind == NIDX_F_KEYS) {
+            cudaMemsetAsync(out, 0, words * 8, stream);
+            auto ar = atom_ranges[i];
+            if (ar.second) {
+                const nidx_vec_segment::InvIndex& ix = s->inv[nd.kind == NIDX_F_LABEL ? NIDX_INV_LABELS : NIDX_INV_FIELDS];
+                bits_scatter_kernel<<<(unsigned)ar.second, 128, 0, stream>>>(ix.d_post, d_ranges + 2 * ar.first, out);
+                LAUNCHED();
+            }
+            *next = i + 1;
+            return out;
+        }
+        int j = i + 1;
+        uint64_t* acc = nullptr;
+        unsigned blocks = (unsigned)std::min<size_t>((words + 255) / 256, 1024);
+        for (int c = 0; c < nd.n; ++c) {
+            int nx;
+            uint64_t* child = eval(j, &nx);
+            j = nx;
+            if (!acc) { cudaMemcpyAsync(out, child, words * 8, cudaMemcpyDeviceToDevice, stream); acc = out; }
+            else {
+                bits_combine_kernel<<<blocks, 256, 0, stream>>>(acc, child, words, s->n_par, nd.kind == NIDX_F_OR ? 1 : 0);   // Not | And => intersect (paragraph.rs:160-164)
+                LAUNCHED();
+            }
+        }
+        if (nd.kind == NIDX_F_NOT) { bits_combine_kernel<<<blocks, 256, 0, stream>>>(acc, nullptr, words, s->n_par, 2); LAUNCHED(); }
+        *next = j;
+        return acc;
+    }
+};
+
+// ParagraphInvertedIndexes::filter on the device: nodes (pre-order; several top-level nodes are not allowed: wrap them in an AND /
+// OR node) -> bitset in `w.filter` (first `words` words), returns the device pointer in *out
+static int filter_formula_device(nidx_vec_segment* s, Workspace& w, const nidx_filter_node* nodes, int n_nodes, cudaStream_t stream, uint64_t** out) {
+    if (!nodes || n_nodes <= 0) return fail(NIDX_EINVAL, "empty filter formula");
+    size_t words = ((size_t)s->n_par + 63) / 64;
+    for (int i = 0; i < n_nodes; ++i) {
+        int kd = nodes[i].kind;
+        if (kd < NIDX_F_LABEL || kd > NIDX_F_NOT || nodes[i].n < 0) return fail(NIDX_EINVAL, "filter node %d: bad kind / count", i);
+        if ((kd == NIDX_F_LABEL || kd == NIDX_F_KEYS) && nodes[i].n > 0 && (!nodes[i].keys || !nodes[i].key_len)) return fail(NIDX_EINVAL, "filter node %d: null keys", i);
+        if ((kd == NIDX_F_AND || kd == NIDX_F_OR || kd == NIDX_F_NOT) && nodes[i].n < 1) return fail(NIDX_EINVAL, "filter node %d: a compound clause needs operands", i);
+    }
+    FilterEval ev;
+    ev.s = s; ev.nodes = nodes; ev.n_nodes = n_nodes; ev.words = words; ev.stream = stream;
+    ev.atom_ranges.assign(n_nodes, {0, 0});
+    if (ev.collect(0) != n_nodes) return fail(NIDX_EINVAL, "malformed filter formula (operand counts do not add up to %d nodes)", n_nodes);
+    size_t range_bytes = ev.ranges.size() * 8;
+    ENSURE(w.filter, ((size_t)n_nodes + 3) * words * 8 + 64 + range_bytes + 64);
+    uint64_t* base = w.filter.as<uint64_t>();
+    ev.bufs = base + 2 * words + 8;          // the first 2 * words + 8 words are vec_search_impl's (filter AND alive, count)
+    ev.d_ranges = ev.bufs + ((size_t)n_nodes + 1) * words;
+    if (range_bytes) CU(cudaMemcpyAsync(ev.d_ranges, ev.ranges.data(), range_bytes, cudaMemcpyHostToDevice, stream));
+    int next = 0;
+    uint64_t* res = ev.eval(0, &next);
+    CU(cudaGetLastError());
+    if (range_bytes) CU(cudaStreamSynchronize(stream));   // `ranges` is a host temporary
+    *out = res;
+    return 0;
+}
+
 // The tensor-core filter + refine path serves large batches of small-k queries on single-vector segments whose rows are whole
 // 128-byte swizzle rows.  NIDX_B200_SCAN=exact forces the CUDA-core kernels (same results, bit for bit), =tensor forces the filter.
 static bool use_tc_filter(const nidx_vec_segment* s, int nq, int k) {
-    if (k > TC2_KMAX || s->ld % TC2_KB != 0 || s->d_par_first || s->n < (uint64_t)TC2_N) return false;
+    if (k > TC2_KMAX || s->ld % TC2_KB != 0 || s->d_par_first || s->n < (uint64_t)TC2_N || s->cfg.similarity == NIDX_SIM_L2) return false;
     const char* e = getenv("NIDX_B200_SCAN");
     if (e && !strcmp(e, "exact")) return false;
     if (e && !strcmp(e, "tensor")) return true;
@@ -659,7 +818,8 @@ static bool use_tc_filter(const nidx_vec_segment* s, int nq, int k) {
 // (copied back and the stream synchronised before returning).  The sharded entry point (shard.cuh) passes host queries with
 // device outputs: the partial results go straight into the exchange buffer.
 static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq, int32_t ldq, bool qhost, bool ohost, const nidx_vec_search_params* p,
-                           uint32_t* out_ids, float* out_scores, int32_t* out_counts, cudaStream_t stream) {
+                           uint32_t* out_ids, float* out_scores, int32_t* out_counts, cudaStream_t stream, const nidx_filter_node* formula = nullptr,
+                           int32_t n_formula = 0) {
     if (!s || !p || (!queries && nq > 0) || !out_ids || !out_scores) return fail(NIDX_EINVAL, "null argument");
     if (nq <= 0) return 0;
     if (ldq < s->d) return fail(NIDX_EINVAL, "query dimension %d != index dimension %d (VectorErr::InconsistentDimensions)", ldq, s->d);
@@ -687,7 +847,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         pad_rows_kernel<<<std::min(nq, 1024), 256, 0, stream>>>(src, (size_t)ldq * 4, s->d, dq, s->ld, (uint64_t)nq);
         LAUNCHED();
     }
-    if (s->cfg.similarity == NIDX_SIM_COSINE) {
+    if (s->cfg.similarity != NIDX_SIM_DOT) {
         row_norms_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(dq, s->ld, (uint64_t)nq, w.qnorms.as<float>());
         LAUNCHED();
     }
@@ -695,20 +855,27 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
     // filter ∧ alive (segment.rs:516-534)
     const uint64_t* bits = s->d_alive;
     size_t words = ((size_t)s->n_par + 63) / 64;
-    uint64_t matching = s->n_par;
-    if (p->filter_bits) {
-        ENSURE(w.filter, words * 8 * 2 + 64);
+    uint64_t matching = s->d_alive ? s->alive_count : s->n_par;
+    const bool filtered = p->filter_bits || formula;
+    if (filtered) {
+        const uint64_t* fsrc = p->filter_bits;
+        bool fhost = host;
+        if (formula) {   // the formula is evaluated on the device (inverted_index/paragraph.rs:124-186): no host bitset, no copy
+            uint64_t* fdev = nullptr;
+            int fr = filter_formula_device(s, w, formula, n_formula, stream, &fdev);
+            if (fr) return fr;
+            fsrc = fdev; fhost = false;
+        } else ENSURE(w.filter, words * 8 * 2 + 64);
         uint64_t* d_in = w.filter.as<uint64_t>();
         uint64_t* d_out = d_in + words;
         unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_out + words);
-        const uint64_t* fsrc = p->filter_bits;
-        if (host) { CU(cudaMemcpyAsync(d_in, p->filter_bits, words * 8, cudaMemcpyHostToDevice, stream)); fsrc = d_in; }
+        if (fhost) { CU(cudaMemcpyAsync(d_in, p->filter_bits, words * 8, cudaMemcpyHostToDevice, stream)); fsrc = d_in; }
         CU(cudaMemsetAsync(d_cnt, 0, 8, stream));
         and_bits_kernel<<<std::min<size_t>((words + 255) / 256, 1024), 256, 0, stream>>>(fsrc, s->d_alive, d_out, words, d_cnt);
         LAUNCHED();
         bits = d_out;
-        matching = p->filter_matching;
-        if (p->method == NIDX_METHOD_AUTO && matching == 0) {
+        matching = formula ? 0 : p->filter_matching;
+        if (matching == 0) {   // segment.rs:531: the reference counts the matches of every filtered request (8 bytes back, one sync)
             unsigned long long h = 0;
             CU(cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
@@ -716,10 +883,23 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         }
     }
 
+    if (matching == 0) {   // segment.rs:532-534: nothing can match (everything deleted / filtered out) -> empty, whatever the method
+        uint32_t* e_ids = out_ids; float* e_sc = out_scores; int* e_cnt = out_counts;
+        if (ohost) {
+            for (size_t i = 0; i < (size_t)nq * k; ++i) { e_ids[i] = NIDX_NIL; e_sc[i] = 0.0f; }
+            if (e_cnt) for (int i = 0; i < nq; ++i) e_cnt[i] = 0;
+            CU(cudaStreamSynchronize(stream));
+        } else {
+            CU(cudaMemsetAsync(e_ids, 0xFF, (size_t)nq * k * 4, stream));
+            CU(cudaMemsetAsync(e_sc, 0, (size_t)nq * k * 4, stream));
+            if (e_cnt) CU(cudaMemsetAsync(e_cnt, 0, (size_t)nq * 4, stream));
+        }
+        return 0;
+    }
     int method = p->method;
     if (method == NIDX_METHOD_AUTO) {
         if (!s->has_graph) method = NIDX_METHOD_BRUTE;
-        else if (matching == 0 && p->filter_bits) method = NIDX_METHOD_BRUTE;
+        else if (matching == 0 && filtered) method = NIDX_METHOD_BRUTE;
         else {
             // a segment that carries codes is searched with a RaBitQ query on either path (segment.rs:506-513: `rabitq` =
             // has_quantized): the quantised walk (hnsw/search.rs:332-366) or the quantised scan (segment.rs:581-608)
@@ -788,15 +968,17 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         CUtensorMap map_q;
         int mr = make_row_tensor_map(&map_q, dq, (uint64_t)nq, s->ld, TC2_M);
         if (mr) return mr;
-        size_t cand_n = (size_t)nq * n_chunks * TC2_L;
+        int grid = std::min(n_chunks * n_qblocks, s->sm_count);
+        int slots = std::max(1, std::min(grid / n_qblocks, n_chunks));   // CTAs per query block; 1 when there are more blocks than CTAs
+        size_t cand_n = (size_t)nq * slots * TC2_L;
         ENSURE(w.scores, cand_n * 8 + 64);
         ENSURE(w.sched, 64);
         Tc2Args ta;
-        ta.nq = nq; ta.n_qblocks = n_qblocks; ta.n_chunks = n_chunks; ta.qnorms = w.qnorms.as<float>(); ta.bits = bits;
+        ta.nq = nq; ta.n_qblocks = n_qblocks; ta.n_chunks = n_chunks; ta.slots = slots; ta.qnorms = w.qnorms.as<float>(); ta.bits = bits;
         ta.cand_score = w.scores.as<float>(); ta.cand_id = reinterpret_cast<uint32_t*>(w.scores.as<float>() + cand_n);
         ta.work_counter = w.sched.as<unsigned int>();
         CU(cudaFuncSetAttribute(scan_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
-        int grid = std::min(n_chunks * n_qblocks, s->sm_count);
+        grid = n_qblocks <= grid ? n_qblocks * slots : grid;
         CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
         CU(cudaEventRecord(s->ev_k0, stream));
         scan_tc_filter_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, stream>>>(map_q, s->map_v, V, ta);
@@ -805,7 +987,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         int cap = topk_cap(k, 256);
         size_t smem_rf = tc2_refine_smem(s->ld, cap);
         if (smem_rf > 48 * 1024) CU(cudaFuncSetAttribute(scan_tc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rf));
-        scan_tc_refine_kernel<<<nq, 256, smem_rf, stream>>>(V, dq, w.qnorms.as<float>(), n_chunks, ta.cand_score, ta.cand_id, bits, s->max_norm, p->min_score, k, cap,
+        scan_tc_refine_kernel<<<nq, 256, smem_rf, stream>>>(V, dq, w.qnorms.as<float>(), slots, ta.cand_score, ta.cand_id, bits, s->max_norm, p->min_score, k, cap,
                                                             d_ids, d_sc, d_cnt, s->d_counters + 6);
         LAUNCHED();
         CU(cudaGetLastError());
@@ -950,6 +1132,58 @@ int nidx_vec_search(nidx_vec_segment* s, const float* queries, int32_t nq, int32
                     float* out_scores, int32_t* out_counts, void* stream_) {
     bool host = mem == NIDX_MEM_HOST;
     return vec_search_impl(s, queries, nq, ldq, host, host, p, out_ids, out_scores, out_counts, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+int nidx_vec_search_formula(nidx_vec_segment* s, const float* queries, int32_t nq, int32_t ldq, int mem, const nidx_vec_search_params* p,
+                            const nidx_filter_node* nodes, int32_t n_nodes, uint32_t* out_ids, float* out_scores, int32_t* out_counts, void* stream_) {
+    bool host = mem == NIDX_MEM_HOST;
+    if (p && p->filter_bits) return fail(NIDX_EINVAL, "give either filter_bits or a formula");
+    return vec_search_impl(s, queries, nq, ldq, host, host, p, out_ids, out_scores, out_counts, reinterpret_cast<cudaStream_t>(stream_), nodes, n_nodes);
+}
+
+int nidx_vec_set_inverted_index(nidx_vec_segment* s, int32_t which, uint32_t n_keys, const uint8_t* key_bytes, const uint64_t* key_off, const uint64_t* post_off,
+                                const uint32_t* postings) {
+    if (!s || (which != NIDX_INV_LABELS && which != NIDX_INV_FIELDS)) return fail(NIDX_EINVAL, "bad argument");
+    if (n_keys && (!key_off || !post_off || (!key_bytes && key_off[n_keys]) || (!postings && post_off[n_keys]))) return fail(NIDX_EINVAL, "null argument");
+    CU(cudaSetDevice(s->cfg.device));
+    nidx_vec_segment::InvIndex& ix = s->inv[which];
+    cudaFree(ix.d_post); ix.d_post = nullptr; ix.n_keys = 0;
+    if (!n_keys) { ix.key_bytes.clear(); ix.key_off.assign(1, 0); ix.post_off.assign(1, 0); return 0; }
+    for (uint32_t i = 0; i + 1 < n_keys; ++i)
+        if (FilterEval::cmp_key(key_bytes + key_off[i], key_off[i + 1] - key_off[i], key_bytes + key_off[i + 1], key_off[i + 2] - key_off[i + 1]) >= 0)
+            return fail(NIDX_EINVAL, "inverted index keys must be strictly ascending (key %u)", i + 1);
+    uint64_t np = post_off[n_keys];
+    for (uint64_t i = 0; i < np; ++i) if (postings[i] >= s->n_par) return fail(NIDX_EINVAL, "posting %llu: paragraph %u out of range", (unsigned long long)i, postings[i]);
+    ix.key_bytes.assign(key_bytes, key_bytes + key_off[n_keys]);
+    ix.key_off.assign(key_off, key_off + n_keys + 1);
+    ix.post_off.assign(post_off, post_off + n_keys + 1);
+    CU(cudaMalloc(&ix.d_post, std::max<uint64_t>(np, 1) * 4));
+    if (np) CU(cudaMemcpy(ix.d_post, postings, np * 4, cudaMemcpyHostToDevice));
+    ix.n_keys = n_keys;
+    return 0;
+}
+
+int nidx_vec_filter(nidx_vec_segment* s, const nidx_filter_node* nodes, int32_t n_nodes, uint64_t* out_bits, int mem, uint64_t* out_matching, void* stream_) {
+    if (!s) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(s->cfg.device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    WsGuard g(s->pool, stream);
+    Workspace& w = *g.w;
+    uint64_t* fdev = nullptr;
+    int r = filter_formula_device(s, w, nodes, n_nodes, stream, &fdev);
+    if (r) return r;
+    size_t words = ((size_t)s->n_par + 63) / 64;
+    uint64_t* d_out = w.filter.as<uint64_t>() + words;
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_out + words);
+    CU(cudaMemsetAsync(d_cnt, 0, 8, stream));
+    and_bits_kernel<<<std::min<size_t>((words + 255) / 256, 1024), 256, 0, stream>>>(fdev, s->d_alive, d_out, words, d_cnt);   // segment.rs:523-526: intersect with the alive set
+    LAUNCHED();
+    if (out_bits) CU(cudaMemcpyAsync(out_bits, d_out, words * 8, mem == NIDX_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, stream));
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    if (out_matching) *out_matching = h;
+    return 0;
 }
 
 int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, int32_t n_parts, int64_t part_stride, int32_t nq, int32_t k,
@@ -1306,6 +1540,21 @@ int nidx_vec_open(const nidx_vec_config* cfg, const char* dir, nidx_vec_segment*
         s->entry_node = fg.entry_node;   // the file's entry point (ram_hnsw.rs: hash-order dependent in the reference)
         s->entry_layer = fg.entry_layer;
     }
+    // vectors.quant (data_store/v2/quant_vector_store.rs:29-62): the RaBitQ codes, one record of dim / 8 + 8 bytes per vector, loaded as they
+    // are (re-laid out to the 16-byte stride in HBM) instead of re-encoding
+    std::vector<unsigned char> quant;
+    if (s->cfg.similarity == NIDX_SIM_DOT && s->d % 64 == 0 && s->d / 32 <= RQ_MAX_WORDS32 && segio::read_file(std::string(dir) + "/vectors.quant", quant, err) && !quant.empty()) {
+        size_t rec_q = (size_t)s->d / 8 + 8;
+        if (quant.size() != rec_q * n) { nidx_vec_close(s); return fail(NIDX_EIO, "vectors.quant holds %zu bytes, expected %zu records of %zu", quant.size(), (size_t)n, rec_q); }
+        s->quant_stride = rabitq_stride(s->d);
+        r = [&]() -> int {
+            CU(cudaMalloc(&s->d_quant, std::max<size_t>((size_t)n * s->quant_stride, 16)));
+            CU(cudaMemset(s->d_quant, 0, std::max<size_t>((size_t)n * s->quant_stride, 16)));
+            CU(cudaMemcpy2D(s->d_quant, (size_t)s->quant_stride, quant.data(), rec_q, rec_q, (size_t)n, cudaMemcpyHostToDevice));
+            return 0;
+        }();
+        if (r) { nidx_vec_close(s); return r; }
+    }
     *out = s;
     return 0;
 }
@@ -1332,6 +1581,16 @@ int nidx_vec_save(nidx_vec_segment* s, const char* dir) {
         int r = nidx_vec_get_graph(s, nullptr, fg.adj0.data(), fg.w0.data(), fg.adjU.data(), fg.wU.data());
         if (r) return r;
         if (!segio::write_graph_v2(std::string(dir) + "/hnsw.graph", std::string(dir) + "/hnsw.edges", fg, err)) return fail(NIDX_EIO, "%s", err.c_str());
+    }
+    if (s->d_quant) {   // vectors.quant: QuantVectorStoreWriter (quant_vector_store.rs), records back to back
+        size_t rec_q = (size_t)s->d / 8 + 8;
+        std::vector<unsigned char> quant(rec_q * n);
+        if (n) CU(cudaMemcpy2D(quant.data(), rec_q, s->d_quant, (size_t)s->quant_stride, rec_q, (size_t)n, cudaMemcpyDeviceToHost));
+        FILE* f = fopen((std::string(dir) + "/vectors.quant").c_str(), "wb");
+        if (!f) return fail(NIDX_EIO, "cannot write %s/vectors.quant", dir);
+        size_t wr = quant.empty() ? 0 : fwrite(quant.data(), 1, quant.size(), f);
+        fclose(f);
+        if (wr != quant.size()) return fail(NIDX_EIO, "short write to %s/vectors.quant", dir);
     }
     return 0;
 }

@@ -12,11 +12,11 @@
 namespace nidx {
 
 constexpr uint32_t NIL = 0xFFFFFFFFu;
-constexpr int SIM_DOT = 0, SIM_COSINE = 1;
+constexpr int SIM_DOT = 0, SIM_COSINE = 1, SIM_L2 = 2;   // L2: an extension (the reference has Dot and Cosine only, config.rs:33-37)
 
 struct VecDev {
     const float* vecs;    // [n][ld] f32, ld % 4 == 0, rows 16-byte aligned, zero padded
-    const float* norms;   // [n] sqrt(dot_ordered(v, v)); read only for cosine
+    const float* norms;   // [n] sqrt(dot_ordered(v, v)); read for cosine and L2
     const uint32_t* paragraph_of;  // [n] or nullptr (identity)
     uint32_t n;
     int d, ld, sim;
@@ -137,8 +137,16 @@ __device__ __forceinline__ float cosine_from_parts(float ab, float na, float nb)
     return __fsub_rn(1.0f, dist);
 }
 
+// L2 as a similarity (higher = closer): -|a - b|^2 = 2 ab - (|a|^2 + |b|^2), from the same ordered dot and the stored norms
+// (|x|^2 is taken as rn(|x| * |x|), the same on the oracle's side), so it ranks like every other similarity here.
+__device__ __forceinline__ float l2_from_parts(float ab, float na, float nb) {
+    return __fsub_rn(__fmul_rn(2.0f, ab), __fadd_rn(__fmul_rn(na, na), __fmul_rn(nb, nb)));
+}
+__device__ __forceinline__ float sim_from_parts(int sim, float ab, float na, float nb) {
+    return sim == SIM_COSINE ? cosine_from_parts(ab, na, nb) : (sim == SIM_L2 ? l2_from_parts(ab, na, nb) : ab);
+}
 __device__ __forceinline__ float finish_similarity(const VecDev& V, float ab, uint32_t x, float qnorm) {
-    return V.sim == SIM_COSINE ? cosine_from_parts(ab, V.norms[x], qnorm) : ab;
+    return V.sim == SIM_DOT ? ab : sim_from_parts(V.sim, ab, V.norms[x], qnorm);
 }
 
 }  // namespace nidx

@@ -95,7 +95,7 @@ __device__ inline int select_neighbours_heuristic(const VecDev& V, HeurSmem& h, 
             int j = p - i * (i - 1) / 2;
             float ab = warp_dot_ss(reinterpret_cast<const float4*>(h.cache + (size_t)i * V.ld), reinterpret_cast<const float4*>(h.cache + (size_t)j * V.ld), ng, lane);
             if (lane == 0) {
-                float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, V.norms[h.cand_id[i]], V.norms[h.cand_id[j]]) : ab;
+                float s = sim_from_parts(V.sim, ab, V.norms[h.cand_id[i]], V.norms[h.cand_id[j]]);
                 h.pair[i * HB_PAIR_LD + j] = s;
                 h.pair[j * HB_PAIR_LD + i] = s;
             }
@@ -129,13 +129,13 @@ __device__ inline int select_neighbours_heuristic(const VecDev& V, HeurSmem& h, 
         if (threadIdx.x == 0) *h.s_fail = 0;
         __syncthreads();
         const float4* xv = reinterpret_cast<const float4*>(V.vecs + (size_t)x * V.ld);
-        float xn = V.sim == SIM_COSINE ? V.norms[x] : 0.0f;
+        float xn = V.sim != SIM_DOT ? V.norms[x] : 0.0f;
         for (int j = warp; j < nsel; j += HB_WARPS) {  // 72-75: sim(x, new) > sim(x, y) for all kept y
             uint32_t y = h.sel_id[j];
             const float4* yv = j < h.cache_cap ? reinterpret_cast<const float4*>(h.cache + (size_t)j * V.ld)
                                                : reinterpret_cast<const float4*>(V.vecs + (size_t)y * V.ld);
             float ab = warp_dot(xv, yv, ng, lane);
-            float inter = V.sim == SIM_COSINE ? cosine_from_parts(ab, xn, V.norms[y]) : ab;
+            float inter = sim_from_parts(V.sim, ab, xn, V.norms[y]);
             if (lane == 0 && !(sim > inter)) *h.s_fail = 1;
         }
         __syncthreads();

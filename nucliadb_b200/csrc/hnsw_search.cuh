@@ -172,10 +172,10 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
     int ng = V.ld >> 2;
     for (int j = warp; j < ntodo; j += HS_WARPS) {
         uint32_t y = c.todo_id[j];
-        float vnorm = V.sim == SIM_COSINE ? __ldg(V.norms + y) : 0.0f;
+        float vnorm = V.sim != SIM_DOT ? __ldg(V.norms + y) : 0.0f;
         float ab = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)y * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
         if (lane == 0) {
-            float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, vnorm, c.qnorm) : ab;
+            float s = sim_from_parts(V.sim, ab, vnorm, c.qnorm);
             uint64_t key = make_key(s, y, 1);
             bool admit = CU ? (s >= min_score) : (key > wkey);
             c.todo_key[j] = admit ? key : 0;
@@ -368,8 +368,8 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
 
         const float* qsrc;
         uint32_t self = NIL;
-        if (a.mode == 0) { qsrc = a.queries + (size_t)q * V.ld; c.qnorm = V.sim == SIM_COSINE ? a.qnorms[q] : 0.0f; }
-        else { self = a.nodes[q]; qsrc = V.vecs + (size_t)self * V.ld; c.qnorm = V.sim == SIM_COSINE ? V.norms[self] : 0.0f; }
+        if (a.mode == 0) { qsrc = a.queries + (size_t)q * V.ld; c.qnorm = V.sim != SIM_DOT ? a.qnorms[q] : 0.0f; }
+        else { self = a.nodes[q]; qsrc = V.vecs + (size_t)self * V.ld; c.qnorm = V.sim != SIM_DOT ? V.norms[self] : 0.0f; }
         for (int i = threadIdx.x; i < ng; i += blockDim.x) reinterpret_cast<float4*>(c.qvec)[i] = reinterpret_cast<const float4*>(qsrc)[i];
         __syncthreads();
 

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_scores_kernel(VecDev V, 
     for (int j = 0; j < nv; ++j) {
         uint32_t v = (uint32_t)(v0 + j);
         const float4* a = reinterpret_cast<const float4*>(V.vecs + (size_t)v * V.ld);
-        float vnorm = V.sim == SIM_COSINE ? V.norms[v] : 0.0f;
+        float vnorm = V.sim != SIM_DOT ? V.norms[v] : 0.0f;
         if (ng <= 256) {
             float4 va[8];  // the whole row, lane-sliced, read from HBM once for all queries of the tile
 #pragma unroll
@@ -94,14 +94,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_scores_kernel(VecDev V, 
                         }
                     }
                     float ab = butterfly_sum(__fadd_rn(__fadd_rn(ax, ay), __fadd_rn(az, aw)));
-                    float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, vnorm, qnorms[q0 + qi]) : ab;
+                    float s = sim_from_parts(V.sim, ab, vnorm, qnorms[q0 + qi]);
                     if (lane == j) mine[qi] = s;
                 }
             }
         } else {
             for (int qi = 0; qi < nqt; ++qi) {
                 float ab = warp_dot(a, reinterpret_cast<const float4*>(qs) + (size_t)qi * ng, ng, lane);
-                float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, vnorm, qnorms[q0 + qi]) : ab;
+                float s = sim_from_parts(V.sim, ab, vnorm, qnorms[q0 + qi]);
                 if (lane == j) mine[qi] = s;
             }
         }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_scores_kernel_t(VecDev V
             const float4* a = reinterpret_cast<const float4*>(V.vecs + (size_t)v * V.ld);
 #pragma unroll
             for (int t = 0; t < NG; ++t) va[u][t] = ldg_stream(a + t * 32 + lane);
-            vnorm[u] = V.sim == SIM_COSINE ? __ldg(V.norms + v) : 0.0f;
+            vnorm[u] = V.sim != SIM_DOT ? __ldg(V.norms + v) : 0.0f;
         }
 #pragma unroll
         for (int qi = 0; qi < SCAN_QT; ++qi) {
@@ -162,11 +162,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) scan_scores_kernel_t(VecDev V
                         acc[u][3] = __fmaf_rn(va[u][t].w, vb.w, acc[u][3]);
                     }
                 }
-                float qn = V.sim == SIM_COSINE ? qnorms[q0 + qi] : 0.0f;
+                float qn = V.sim != SIM_DOT ? qnorms[q0 + qi] : 0.0f;
 #pragma unroll
                 for (int u = 0; u < VU; ++u) {
                     float ab = butterfly_sum(__fadd_rn(__fadd_rn(acc[u][0], acc[u][1]), __fadd_rn(acc[u][2], acc[u][3])));
-                    float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, vnorm[u], qn) : ab;
+                    float s = sim_from_parts(V.sim, ab, vnorm[u], qn);
                     if (lane == j0 + u) mine[qi] = s;
                 }
             }

@@ -8,20 +8,23 @@
 // and to the oracle (round 1's 3xTF32 kernel was 1e-6 off and materialised the [Q x N] matrix).
 //
 //   |tf32(q) . tf32(v) - q . v| <= 2^-9 |q| |v|  (each operand keeps 10 mantissa bits: relative error < 2^-10 per factor)
-//   eps = 2.2e-3 (cosine) or 2.2e-3 |q| max|v| (dot).  For a vector chunk C and a query, every eligible v in C that belongs
-//   to the true top-k has approx(v) >= (k-th largest approx in C) - 2 eps; so a chunk emits its best TC2_L candidates, and a
-//   chunk whose L-th candidate is still inside that margin is an OVERFLOW (the query is then scanned exactly: rare).
-//   Over all chunks: tau = k-th largest approx among the candidates; survivors = candidates with approx >= tau - 2 eps.
+//   eps = 2.2e-3 (cosine) or 2.2e-3 |q| max|v| (dot).  Let tau = the k-th largest APPROXIMATE score of a query over the
+//   eligible vectors: every member of the true top-k has approx >= tau - 2 eps.  Each CTA keeps, per query row, the best
+//   TC2_L approximate scores of ITS share of the vectors (a list in registers); the k best approximations overall are in
+//   those lists (at most k - 1 entries of a share rank above any of them, and L >= k), so tau is known exactly from the
+//   lists; survivors = list entries with approx >= tau - 2 eps.  A list that is full and whose smallest entry is still
+//   >= tau - 2 eps may have dropped a survivor: OVERFLOW, the query is then scanned exactly (rare).
 //
-// scan_tc_filter_kernel: persistent CTAs over (vector chunk, 128-query block) items, query block fastest (CTAs that run
-// together share the chunk: L2 reuse).  Warp-specialised, Blackwell-native:
+// scan_tc_filter_kernel: persistent CTAs; a CTA serves ONE 128-query block (slot s of grid / n_qblocks slots) and walks the
+// vector chunks s, s + slots, ...; the CTAs of one slot run together and share every chunk (L2 reuse).  Warp-specialised:
 //   warp 0   TMA producer: cp.async.bulk.tensor (128-byte swizzle) of a 128 x 32-float query tile and a 256 x 32-float
 //            vector tile per stage into a 4-stage mbarrier ring (48 KB per stage);
 //   warp 1   MMA issuer: one thread, tcgen05.mma.cta_group::1.kind::tf32, M = 128 (queries) x N = 256 (vectors) x K = 8,
 //            four per stage; tcgen05.commit releases the stage; accumulators double-buffered in TMEM (2 x 256 columns);
 //   warp 2   TMEM allocation;
 //   warps 4-7 epilogue: thread = query row = TMEM lane; tcgen05.ld 32 columns at a time, cosine scaling, eligibility bit,
-//            streaming top-L list of the row in shared memory (insertion only when a score beats the row's L-th best).
+//            running top-L of the row in REGISTERS (unsorted + its minimum; the update is branch-free and entered only when a
+//            lane of the warp has a score above its row's minimum).
 // scan_tc_refine_kernel: one CTA per query: overflow test, tau, survivors, exact re-scoring (one warp per survivor),
 //   min_score, top-k -- or the exact scan of the whole segment for an overflowed query.
 #pragma once
@@ -43,7 +46,7 @@ constexpr int TC2_L = 24;             // candidates kept per (query, chunk)
 constexpr int TC2_KMAX = 16;          // the filter path serves k <= TC2_KMAX
 constexpr int TC2_THREADS = 256;
 constexpr uint32_t TC2_A_BYTES = TC2_M * 128, TC2_B_BYTES = TC2_N * 128, TC2_STAGE_BYTES = TC2_A_BYTES + TC2_B_BYTES;
-constexpr size_t TC2_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)TC2_STAGES * TC2_STAGE_BYTES + (size_t)TC2_M * TC2_L * 8 + 2 * TC2_N * 4 /* 1/|v| */ +
+constexpr size_t TC2_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)TC2_STAGES * TC2_STAGE_BYTES + 2 * TC2_N * 4 /* 1/|v| */ +
                                   2 * (TC2_N / 32) * 4 /* eligibility */ + 256;
 constexpr float TC2_EPS = 2.2e-3f;
 constexpr int TC2_SURV_CAP = 512;     // survivors per query the refine kernel re-scores; more => exact scan
@@ -68,12 +71,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 
 struct Tc2Args {
-    int nq, n_qblocks, n_chunks;
+    int nq, n_qblocks, n_chunks, slots;   // slots = CTAs per query block (1 when there are more query blocks than CTAs)
     const float* qnorms;          // [nq] (cosine)
     const uint64_t* bits;         // eligibility (alive & filter) per vector, or nullptr
-    float* cand_score;            // [nq][n_chunks][TC2_L] approx scores, descending, -inf padded
-    uint32_t* cand_id;            // [nq][n_chunks][TC2_L]
+    float* cand_score;            // [nq][slots][TC2_L] approx scores, unsorted, -inf padded
+    uint32_t* cand_id;            // [nq][slots][TC2_L]
     unsigned int* work_counter;
+};
+
+// The (query block, chunk) sequence of a CTA -- the same in the three roles.  n_qblocks <= gridDim: CTA c serves block c % n_qblocks
+// as slot c / n_qblocks (CTAs beyond n_qblocks * slots idle); else one slot and CTA c serves blocks c, c + gridDim, ...
+struct Tc2Sched {
+    int g0, gstride, slot, slots;
+    __device__ Tc2Sched(const Tc2Args& a) {
+        slots = a.slots;
+        if (a.n_qblocks <= (int)gridDim.x) { g0 = (int)blockIdx.x % a.n_qblocks; slot = (int)blockIdx.x / a.n_qblocks; gstride = a.n_qblocks; if (slot >= slots) g0 = a.n_qblocks; }
+        else { g0 = (int)blockIdx.x; slot = 0; gstride = (int)gridDim.x; }
+    }
 };
 
 __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_v,
@@ -81,16 +95,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
     extern __shared__ unsigned char tc2_raw[];
     __shared__ uint64_t full[TC2_STAGES], empty[TC2_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ int s_item[2];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)tc2_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles: 1024-byte aligned
     unsigned char* stages = smem;
-    float* l_score = reinterpret_cast<float*>(smem + (size_t)TC2_STAGES * TC2_STAGE_BYTES);   // [128][L]
-    uint32_t* l_id = reinterpret_cast<uint32_t*>(l_score + TC2_M * TC2_L);
-    float* inv_vn = reinterpret_cast<float*>(l_id + TC2_M * TC2_L);                            // [2][256]
+    float* inv_vn = reinterpret_cast<float*>(smem + (size_t)TC2_STAGES * TC2_STAGE_BYTES);     // [2][256]
     uint32_t* elig = reinterpret_cast<uint32_t*>(inv_vn + 2 * TC2_N);                          // [2][8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = V.ld / TC2_KB;
-    const int n_items = a.n_chunks * a.n_qblocks;
+    const Tc2Sched sch(a);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -107,26 +118,24 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
 
-    // Static round-robin over the items: every role computes the same sequence (item = blockIdx.x + i * gridDim.x).
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t st = 0, ph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int qb = item % a.n_qblocks, ch = item / a.n_qblocks;
-                for (int t = 0; t < TC2_TILES; ++t) {
-                    int v0 = ch * TC2_CHUNK + t * TC2_N;
-                    if ((uint32_t)v0 >= V.n) break;
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        mbar_wait(&empty[st], ph ^ 1);
-                        mbar_expect_tx(&full[st], TC2_STAGE_BYTES);
-                        unsigned char* sa = stages + (size_t)st * TC2_STAGE_BYTES;
-                        tma_load_2d(sa, &map_q, kb * TC2_KB, qb * TC2_M, &full[st]);
-                        tma_load_2d(sa + TC2_A_BYTES, &map_v, kb * TC2_KB, v0, &full[st]);
-                        if (++st == TC2_STAGES) { st = 0; ph ^= 1; }
+            for (int qb = sch.g0; qb < a.n_qblocks; qb += sch.gstride)
+                for (int ch = sch.slot; ch < a.n_chunks; ch += sch.slots)
+                    for (int t = 0; t < TC2_TILES; ++t) {
+                        int v0 = ch * TC2_CHUNK + t * TC2_N;
+                        if ((uint32_t)v0 >= V.n) break;
+                        for (int kb = 0; kb < n_kb; ++kb) {
+                            mbar_wait(&empty[st], ph ^ 1);
+                            mbar_expect_tx(&full[st], TC2_STAGE_BYTES);
+                            unsigned char* sa = stages + (size_t)st * TC2_STAGE_BYTES;
+                            tma_load_2d(sa, &map_q, kb * TC2_KB, qb * TC2_M, &full[st]);
+                            tma_load_2d(sa + TC2_A_BYTES, &map_v, kb * TC2_KB, v0, &full[st]);
+                            if (++st == TC2_STAGES) { st = 0; ph ^= 1; }
+                        }
                     }
-                }
-            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -134,101 +143,111 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
             const uint32_t idesc = tc2_idesc();
             const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stages);
             uint32_t st = 0, ph = 0, tcount = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int ch = item / a.n_qblocks;
-                for (int t = 0; t < TC2_TILES; ++t) {
-                    int v0 = ch * TC2_CHUNK + t * TC2_N;
-                    if ((uint32_t)v0 >= V.n) break;
-                    uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-                    mbar_wait(&tmem_empty[acc], aph ^ 1);               // the epilogue has drained this accumulator
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        mbar_wait(&full[st], ph);
+            for (int qb = sch.g0; qb < a.n_qblocks; qb += sch.gstride)
+                for (int ch = sch.slot; ch < a.n_chunks; ch += sch.slots)
+                    for (int t = 0; t < TC2_TILES; ++t) {
+                        int v0 = ch * TC2_CHUNK + t * TC2_N;
+                        if ((uint32_t)v0 >= V.n) break;
+                        uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                        mbar_wait(&tmem_empty[acc], aph ^ 1);               // the epilogue has drained this accumulator
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        uint32_t sa = sbase + st * TC2_STAGE_BYTES, sb = sa + TC2_A_BYTES;
+                        for (int kb = 0; kb < n_kb; ++kb) {
+                            mbar_wait(&full[st], ph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            uint32_t sa = sbase + st * TC2_STAGE_BYTES, sb = sa + TC2_A_BYTES;
 #pragma unroll
-                        for (int ks = 0; ks < TC2_KB / 8; ++ks)    // K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                            tc_mma(tmem_d + acc * TC2_N, tc2_desc(sa + ks * 32), tc2_desc(sb + ks * 32), idesc, (kb | ks) != 0);
-                        tc_commit(&empty[st]);                          // frees the stage when these MMAs have read it
-                        if (++st == TC2_STAGES) { st = 0; ph ^= 1; }
+                            for (int ks = 0; ks < TC2_KB / 8; ++ks)    // K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                                tc_mma(tmem_d + acc * TC2_N, tc2_desc(sa + ks * 32), tc2_desc(sb + ks * 32), idesc, (kb | ks) != 0);
+                            tc_commit(&empty[st]);                          // frees the stage when these MMAs have read it
+                            if (++st == TC2_STAGES) { st = 0; ph ^= 1; }
+                        }
+                        tc_commit(&tmem_full[acc]);                         // accumulator complete
+                        ++tcount;
                     }
-                    tc_commit(&tmem_full[acc]);                         // accumulator complete
-                    ++tcount;
-                }
-            }
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread = query row =====
         const int row = (warp & 3) * 32 + lane;
         const int et = threadIdx.x - 128;   // 0..127
-        float* my_s = l_score + row * TC2_L;
-        uint32_t* my_i = l_id + row * TC2_L;
         uint32_t tcount = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            int qb = item % a.n_qblocks, ch = item / a.n_qblocks;
+        for (int qb = sch.g0; qb < a.n_qblocks; qb += sch.gstride) {
             int q = qb * TC2_M + row;
             float inv_qn = 1.0f;
             if (V.sim == SIM_COSINE) { float qn = q < a.nq ? a.qnorms[q] : 0.0f; inv_qn = qn > 0.0f ? __frcp_rn(qn) : 0.0f; }
-            int cnt = 0;
-            float thr = -INFINITY;       // the row's L-th best so far (-inf until the list is full)
-            for (int t = 0; t < TC2_TILES; ++t) {
-                int v0 = ch * TC2_CHUNK + t * TC2_N;
-                if ((uint32_t)v0 >= V.n) break;
-                uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-                // per-tile column data: 1 / |v| (cosine) and the eligibility bits, by the 128 epilogue threads
-                for (int j = et; j < TC2_N; j += 128) {
-                    uint32_t v = (uint32_t)v0 + j;
-                    float ivn = 1.0f;
-                    if (V.sim == SIM_COSINE) { float vn = v < V.n ? __ldg(V.norms + v) : 0.0f; ivn = vn > 0.0f ? __frcp_rn(vn) : 0.0f; }
-                    inv_vn[acc * TC2_N + j] = ivn;
-                }
-                if (et < TC2_N / 32) {
-                    uint32_t w = 0xFFFFFFFFu;
-                    uint32_t vb = (uint32_t)v0 + et * 32;
-                    if (a.bits) w = vb < V.n ? reinterpret_cast<const uint32_t*>(a.bits)[vb >> 5] : 0u;
-                    if (vb + 32 > V.n) w &= vb < V.n ? (0xFFFFFFFFu >> (32 - (V.n - vb))) : 0u;   // columns beyond the segment
-                    elig[acc * (TC2_N / 32) + et] = w;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                mbar_wait(&tmem_full[acc], aph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int c0 = 0; c0 < TC2_N; c0 += 32) {
-                    uint32_t r[32];
-                    uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + acc * TC2_N + c0;
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                                 : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    uint32_t ew = elig[acc * (TC2_N / 32) + (c0 >> 5)];
-                    if (q < a.nq) {
+            // the row's best TC2_L approximate scores over this CTA's share: unsorted, with the minimum and where it sits
+            float ls[TC2_L];
+            uint32_t li[TC2_L];
+#pragma unroll
+            for (int i = 0; i < TC2_L; ++i) { ls[i] = -INFINITY; li[i] = NIL; }
+            int cnt = 0, minpos = 0;
+            float thr = -INFINITY;       // scores <= thr cannot enter the list (-inf until it is full)
+            for (int ch = sch.slot; ch < a.n_chunks; ch += sch.slots)
+                for (int t = 0; t < TC2_TILES; ++t) {
+                    int v0 = ch * TC2_CHUNK + t * TC2_N;
+                    if ((uint32_t)v0 >= V.n) break;
+                    uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                    // per-tile column data: 1 / |v| (cosine) and the eligibility bits, by the 128 epilogue threads
+                    for (int j = et; j < TC2_N; j += 128) {
+                        uint32_t v = (uint32_t)v0 + j;
+                        float ivn = 1.0f;
+                        if (V.sim == SIM_COSINE) { float vn = v < V.n ? __ldg(V.norms + v) : 0.0f; ivn = vn > 0.0f ? __frcp_rn(vn) : 0.0f; }
+                        inv_vn[acc * TC2_N + j] = ivn;
+                    }
+                    if (et < TC2_N / 32) {
+                        uint32_t w = 0xFFFFFFFFu;
+                        uint32_t vb = (uint32_t)v0 + et * 32;
+                        if (a.bits) w = vb < V.n ? reinterpret_cast<const uint32_t*>(a.bits)[vb >> 5] : 0u;
+                        if (vb + 32 > V.n) w &= vb < V.n ? (0xFFFFFFFFu >> (32 - (V.n - vb))) : 0u;   // columns beyond the segment
+                        elig[acc * (TC2_N / 32) + et] = w;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    mbar_wait(&tmem_full[acc], aph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int c0 = 0; c0 < TC2_N; c0 += 32) {
+                        uint32_t r[32];
+                        uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + acc * TC2_N + c0;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                                       "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                                       "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                                     : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        const uint32_t ew = q < a.nq ? elig[acc * (TC2_N / 32) + (c0 >> 5)] : 0u;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            float s = __uint_as_float(r[j]);
-                            if (V.sim == SIM_COSINE) s = s * inv_qn * inv_vn[acc * TC2_N + c0 + j];
-                            if (((ew >> j) & 1u) && s > thr) {
-                                // insert into the row's sorted list (descending); the L-th entry falls off when full
-                                int pos = cnt < TC2_L ? cnt : TC2_L - 1;
-                                while (pos > 0 && my_s[pos - 1] < s) { my_s[pos] = my_s[pos - 1]; my_i[pos] = my_i[pos - 1]; --pos; }
-                                my_s[pos] = s; my_i[pos] = (uint32_t)v0 + c0 + j;
-                                if (cnt < TC2_L) ++cnt;
-                                if (cnt == TC2_L) thr = my_s[TC2_L - 1];
+                            float sc = __uint_as_float(r[j]);
+                            if (V.sim == SIM_COSINE) sc = sc * inv_qn * inv_vn[acc * TC2_N + c0 + j];
+                            const bool pass = ((ew >> j) & 1u) && sc > thr;
+                            if (__any_sync(0xFFFFFFFFu, pass)) {          // warp-uniform: most columns beat no row's minimum
+                                if (pass) {
+                                    const int pos = cnt < TC2_L ? cnt : minpos;
+                                    const uint32_t id = (uint32_t)v0 + c0 + j;
+#pragma unroll
+                                    for (int i = 0; i < TC2_L; ++i) if (i == pos) { ls[i] = sc; li[i] = id; }   // static indices: predicated moves
+                                    if (cnt < TC2_L) ++cnt;
+                                    if (cnt == TC2_L) {
+                                        float m = ls[0];
+                                        int mp = 0;
+#pragma unroll
+                                        for (int i = 1; i < TC2_L; ++i) if (ls[i] < m) { m = ls[i]; mp = i; }
+                                        thr = m; minpos = mp;
+                                    }
+                                }
                             }
                         }
                     }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    ++tcount;
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                ++tcount;
-            }
             if (q < a.nq) {
-                float* os = a.cand_score + ((size_t)q * a.n_chunks + ch) * TC2_L;
-                uint32_t* oi = a.cand_id + ((size_t)q * a.n_chunks + ch) * TC2_L;
-                for (int i = 0; i < TC2_L; ++i) { os[i] = i < cnt ? my_s[i] : -INFINITY; oi[i] = i < cnt ? my_i[i] : NIL; }
+                float* os = a.cand_score + ((size_t)q * a.slots + sch.slot) * TC2_L;
+                uint32_t* oi = a.cand_id + ((size_t)q * a.slots + sch.slot) * TC2_L;
+#pragma unroll
+                for (int i = 0; i < TC2_L; ++i) { os[i] = ls[i]; oi[i] = li[i]; }
             }
         }
     }
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
 // One CTA per query.  dynamic smem: ld floats (query) + cap keys (top-k buffer) + survivors.
 __host__ __device__ __forceinline__ size_t tc2_refine_smem(int ld, int cap) { return (size_t)ld * 4 + (size_t)cap * 8 + (size_t)TC2_SURV_CAP * 4 + 64; }
 
-__global__ void __launch_bounds__(256) scan_tc_refine_kernel(VecDev V, const float* __restrict__ queries, const float* __restrict__ qnorms, int n_chunks,
+__global__ void __launch_bounds__(256) scan_tc_refine_kernel(VecDev V, const float* __restrict__ queries, const float* __restrict__ qnorms, int n_lists,
                                                              const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_id,
                                                              const uint64_t* __restrict__ bits, float max_vnorm, float min_score, int k, int cap,
                                                              uint32_t* __restrict__ out_ids, float* __restrict__ out_scores, int* __restrict__ out_counts,
@@ -268,15 +287,10 @@ __global__ void __launch_bounds__(256) scan_tc_refine_kernel(VecDev V, const flo
     if (threadIdx.x == 0) { s_overflow = (V.sim == SIM_COSINE && !(qn > 0.0f)) ? 1 : 0; s_nsurv = 0; }
     BlockTopK tk;
     tk.init(tk_buf, &tk_count, &tk_thr, k, cap);
-    const float* cs = cand_score + (size_t)q * n_chunks * TC2_L;
-    const uint32_t* ci = cand_id + (size_t)q * n_chunks * TC2_L;
-    // 1. overflow test per chunk list: full, and its last entry still within the margin of its k-th
-    for (int ch = threadIdx.x; ch < n_chunks; ch += blockDim.x) {
-        const float* l = cs + (size_t)ch * TC2_L;
-        if (l[TC2_L - 1] != -INFINITY && l[TC2_L - 1] >= l[k - 1] - margin) s_overflow = 1;
-    }
-    // 2. tau = k-th largest approximate score among all candidates
-    const int total = n_chunks * TC2_L;
+    const float* cs = cand_score + (size_t)q * n_lists * TC2_L;
+    const uint32_t* ci = cand_id + (size_t)q * n_lists * TC2_L;
+    // 1. tau = k-th largest approximate score among all candidates
+    const int total = n_lists * TC2_L;
     for (int base = 0; base < total; base += blockDim.x) {
         int i = base + threadIdx.x;
         uint64_t key = 0;
@@ -286,6 +300,13 @@ __global__ void __launch_bounds__(256) scan_tc_refine_kernel(VecDev V, const flo
     int c = tk.finish();
     const float tau = c >= k ? key_score(tk_buf[k - 1]) : -INFINITY;
     __syncthreads();
+    // 2. overflow test per list: full (no NIL entry), and its smallest entry still within the margin of tau
+    for (int l = threadIdx.x; l < n_lists; l += blockDim.x) {
+        float mn = INFINITY;
+        bool full = true;
+        for (int i = 0; i < TC2_L; ++i) { full &= ci[(size_t)l * TC2_L + i] != NIL; mn = fminf(mn, cs[(size_t)l * TC2_L + i]); }
+        if (full && mn >= tau - margin) s_overflow = 1;
+    }
     // 3. survivors
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         if (ci[i] != NIL && cs[i] >= tau - margin) {
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(256) scan_tc_refine_kernel(VecDev V, const flo
                 bool ok = !exact_all || !bits || ((bits[v >> 6] >> (v & 63)) & 1);
                 if (ok) {
                     float ab = warp_dot(reinterpret_cast<const float4*>(V.vecs + (size_t)v * V.ld), reinterpret_cast<const float4*>(qv), ng, lane);
-                    float s = V.sim == SIM_COSINE ? cosine_from_parts(ab, V.norms[v], qn) : ab;
+                    float s = sim_from_parts(V.sim, ab, V.norms[v], qn);
                     if (s >= min_score) key = make_key(s, v, 0);
                 }
             }

@@ -29,9 +29,10 @@ from . import _lib
 from ._lib import NIL, NidxError, VecConfig, VecSearchParams, check, ptr
 
 
-class Similarity(enum.Enum):  # config.rs:33-37
+class Similarity(enum.Enum):  # config.rs:33-37 (+ L2: an extension, the reference has no Euclidean similarity)
     Cosine = "Cosine"
     Dot = "Dot"
+    L2 = "L2"
 
 
 class VectorCardinality(enum.Enum):  # config.rs
@@ -60,7 +61,7 @@ class VectorConfig:
     device: int = 0
 
     def _c(self) -> VecConfig:
-        return VecConfig(self.dimension, _lib.NIDX_SIM_COSINE if self.similarity == Similarity.Cosine else _lib.NIDX_SIM_DOT,
+        return VecConfig(self.dimension, {Similarity.Cosine: _lib.NIDX_SIM_COSINE, Similarity.Dot: _lib.NIDX_SIM_DOT, Similarity.L2: _lib.NIDX_SIM_L2}[self.similarity],
                          int(self.vector_cardinality == VectorCardinality.Multi), self.m, self.m0, self.ef_construction, self.ef_search,
                          self.device)
 
@@ -191,6 +192,71 @@ class OpenSegment:
         for p, fk in enumerate(self._field_keys):
             if fk is not None:
                 self._field_index.setdefault(fk, []).append(p)
+        if handle is not None:
+            self._upload_inverted_indexes()
+
+    def _upload_inverted_indexes(self):
+        """ParagraphInvertedIndexes::build (inverted_index/paragraph.rs:74-106): the label and field indexes go to the library --
+        keys sorted bytewise as in the fst, postings to HBM -- so that filter formulas are evaluated on the device."""
+        L = _lib.load()
+        for which, index in ((_lib.NIDX_INV_LABELS, {k.encode(): v for k, v in self._label_index.items()}), (_lib.NIDX_INV_FIELDS, self._field_index)):
+            keys = sorted(index)
+            key_off = np.zeros(len(keys) + 1, dtype=np.uint64)
+            post_off = np.zeros(len(keys) + 1, dtype=np.uint64)
+            if keys:
+                key_off[1:] = np.cumsum([len(k) for k in keys])
+                post_off[1:] = np.cumsum([len(index[k]) for k in keys])
+            key_bytes = np.frombuffer(b"".join(keys) or b"\0", dtype=np.uint8).copy()
+            postings = np.asarray([p for k in keys for p in sorted(index[k])] or [0], dtype=np.uint32)
+            check(L.nidx_vec_set_inverted_index(self._h, C.c_int32(which), C.c_uint32(len(keys)), ptr(key_bytes), ptr(key_off), ptr(post_off), ptr(postings)))
+
+    # -- filter formulas for the device (formula.rs:40-100 -> nidx_filter_node, pre-order) ----------
+    def formula_nodes(self, clauses, operator_and=True):
+        """-> (ctypes array of FilterNode, n, keep-alive list).  Literal -> LABEL(labels_key), _KeyPrefixSet -> KEYS(field keys),
+        Not / Operation -> NOT / AND / OR; several clauses are wrapped in the formula's operator."""
+        flat, keep = [], []
+
+        def atom(kind, keys):
+            bufs = [C.create_string_buffer(k, max(len(k), 1)) for k in keys]      # raw bytes: field keys start with 16 uuid bytes, NULs included
+            arr = (C.c_void_p * max(len(keys), 1))(*[C.addressof(b) for b in bufs])
+            lens = (C.c_uint32 * max(len(keys), 1))(*[len(k) for k in keys])
+            keep.extend([arr, lens, bufs])
+            flat.append((kind, len(keys), arr, lens))
+
+        def walk(c):
+            if isinstance(c, Literal):
+                atom(_lib.NIDX_F_LABEL, [_labels_key(c.value).encode()])
+            elif isinstance(c, _KeyPrefixSet):
+                atom(_lib.NIDX_F_KEYS, [fk for fk in (field_key(f) for f in sorted(c.keys)) if fk is not None])
+            elif isinstance(c, Not):
+                flat.append((_lib.NIDX_F_NOT, 1, None, None))
+                walk(c.operand)
+            elif isinstance(c, Operation):
+                flat.append((_lib.NIDX_F_AND if c.operator == "and" else _lib.NIDX_F_OR, len(c.operands), None, None))
+                for o in c.operands:
+                    walk(o)
+            else:
+                raise TypeError(f"unknown clause {c!r}")
+
+        clauses = list(clauses)
+        if len(clauses) != 1:
+            flat.append((_lib.NIDX_F_AND if operator_and else _lib.NIDX_F_OR, len(clauses), None, None))
+        for c in clauses:
+            walk(c)
+        nodes = (_lib.FilterNode * len(flat))()
+        for i, (kind, n, arr, lens) in enumerate(flat):
+            nodes[i].kind, nodes[i].n = kind, n
+            if arr is not None:
+                nodes[i].keys, nodes[i].key_len = arr, lens
+        return nodes, len(flat), keep
+
+    def device_filter(self, clauses, operator_and=True):
+        """nidx_vec_filter: the formula's bitset AND the alive set, computed on the device -> (bool mask over paragraphs, matching)."""
+        nodes, n, keep = self.formula_nodes(clauses, operator_and)
+        words = np.zeros((self.records + 63) // 64, dtype=np.uint64)
+        matching = C.c_uint64()
+        check(_lib.load().nidx_vec_filter(self._h, nodes, C.c_int32(n), ptr(words), _lib.NIDX_MEM_HOST, C.byref(matching), None))
+        return np.unpackbits(words.view(np.uint8), bitorder="little")[: self.records].astype(bool), int(matching.value)
 
     # -- lifecycle -----------------------------------------------------------------------------
     @classmethod
@@ -334,20 +400,12 @@ class OpenSegment:
         scores = np.empty((nq, top_k), dtype=np.float32)
         counts = np.empty(nq, dtype=np.int32)
         p = VecSearchParams(top_k, ef, min_score, int(with_duplicates), method, None, 0)
-        keep = None
-        mask = self.filter_bitset(list(clauses), operator_and)
-        if mask is not None:
-            matching = int((mask & self.alive).sum())
-            if matching == 0:  # segment.rs:531-534
-                ids.fill(NIL)
-                scores.fill(0)
-                counts.fill(0)
-                return ids, scores, counts
-            bits = np.packbits(mask, bitorder="little")
-            keep = np.zeros((self.records + 63) // 64 * 8, dtype=np.uint8)
-            keep[: len(bits)] = bits
-            p.filter_bits = keep.ctypes.data
-            p.filter_matching = matching
+        clauses = list(clauses)
+        if clauses:   # the formula goes to the library as it is: postings -> bitset -> algebra -> AND alive -> count, all in HBM (segment.rs:516-534)
+            nodes, n_nodes, keep = self.formula_nodes(clauses, operator_and)
+            check(L.nidx_vec_search_formula(self._h, ptr(queries), C.c_int32(nq), C.c_int32(dim), _lib.NIDX_MEM_HOST, C.byref(p), nodes, C.c_int32(n_nodes),
+                                            ptr(ids), ptr(scores), ptr(counts), None))
+            return ids, scores, counts
         check(L.nidx_vec_search(self._h, ptr(queries), C.c_int32(nq), C.c_int32(dim), _lib.NIDX_MEM_HOST, C.byref(p), ptr(ids), ptr(scores), ptr(counts),
                                 None))
         return ids, scores, counts

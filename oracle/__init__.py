@@ -20,7 +20,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 NIL = 0xFFFFFFFF
-SIM_DOT, SIM_COSINE = 0, 1
+SIM_DOT, SIM_COSINE, SIM_L2 = 0, 1, 2
 BM25_OR, BM25_AND = 0, 1
 
 _lib = None
@@ -110,7 +110,7 @@ def brute_force(vecs, queries, k, sim=SIM_COSINE, min_score=-1.0, alive_bits=Non
     vecs, queries = _f32(vecs), _f32(np.atleast_2d(queries))
     n, d = vecs.shape
     nq = queries.shape[0]
-    nrm = norms(vecs, nthreads) if sim == SIM_COSINE else None
+    nrm = norms(vecs, nthreads) if sim != SIM_DOT else None
     n_par = n if first_vec is None else len(first_vec)
     ids = np.empty((nq, k), dtype=np.uint32)
     sc = np.empty((nq, k), dtype=np.float32)
@@ -188,7 +188,7 @@ def hnsw_build(vecs, sim=SIM_COSINE, M=30, M0=60, efC=100, seed=2, max_batch=1, 
     n, d = vecs.shape
     level = assign_levels(n, M, seed) if levels is None else np.ascontiguousarray(levels, dtype=np.uint8)
     g = Graph(n, M, M0, level)
-    nrm = norms(vecs, nthreads) if sim == SIM_COSINE else None
+    nrm = norms(vecs, nthreads) if sim != SIM_DOT else None
     order, ends = default_schedule(n, g.entry_node, max_batch)
     counters = np.zeros(3, dtype=np.uint64)
     secs = lib(native).oracle_hnsw_build(_p(vecs), _p(nrm), C.c_uint32(n), C.c_int(d), C.c_int(d), C.c_int(sim), C.c_int(M), C.c_int(M0),
@@ -235,7 +235,7 @@ def hnsw_extend(vecs, g0: Graph, sim=SIM_COSINE, efC=100, seed=2, max_batch=1, n
     rows0 = int(g0.level.astype(np.int64).sum())
     g.adjU[:rows0], g.wU[:rows0] = g0.adjU[:rows0], g0.wU[:rows0]
     fix_broken_links(g)                         # merge_indexes: index.fix_broken_graph() (segment.rs:162)
-    nrm = norms(vecs, nthreads) if sim == SIM_COSINE else None
+    nrm = norms(vecs, nthreads) if sim != SIM_DOT else None
     # Deviation from the reference, shared with the CUDA path (see nidx_vec_extend_hnsw): a new node that raises the top layer
     # is inserted first, from the old entry point, and only then becomes the entry point -- the reference moves the entry point
     # to the still unlinked node up front (build.rs:49-55), which cuts the reused graph off.
@@ -271,7 +271,7 @@ def hnsw_search(vecs, g: Graph, queries, k, ef, sim=SIM_COSINE, min_score=-1.0, 
     vecs, queries = _f32(vecs), _f32(np.atleast_2d(queries))
     n, d = vecs.shape
     nq = queries.shape[0]
-    nrm = (norms(vecs, nthreads) if norms_ is None else norms_) if sim == SIM_COSINE else None
+    nrm = (norms(vecs, nthreads) if norms_ is None else norms_) if sim != SIM_DOT else None
     ids = np.empty((nq, k), dtype=np.uint32)
     sc = np.empty((nq, k), dtype=np.float32)
     cnt = np.empty(nq, dtype=np.int32)
@@ -287,7 +287,7 @@ def hnsw_search(vecs, g: Graph, queries, k, ef, sim=SIM_COSINE, min_score=-1.0, 
 def layer_search(vecs, g: Graph, query, layer, k, eps, sim=SIM_COSINE):
     vecs, query = _f32(vecs), _f32(query)
     n, d = vecs.shape
-    nrm = norms(vecs) if sim == SIM_COSINE else None
+    nrm = norms(vecs) if sim != SIM_DOT else None
     eps = np.ascontiguousarray(eps, dtype=np.uint32)
     cap = max(k, len(eps))
     ids = np.empty(cap, dtype=np.uint32)
@@ -301,7 +301,7 @@ def layer_search(vecs, g: Graph, query, layer, k, eps, sim=SIM_COSINE):
 def select_neighbours(vecs, k, cand_ids, cand_scores, sim=SIM_COSINE):
     vecs = _f32(vecs)
     n, d = vecs.shape
-    nrm = norms(vecs) if sim == SIM_COSINE else None
+    nrm = norms(vecs) if sim != SIM_DOT else None
     cand_ids = np.ascontiguousarray(cand_ids, dtype=np.uint32)
     cand_scores = _f32(cand_scores)
     ids = np.empty(len(cand_ids), dtype=np.uint32)

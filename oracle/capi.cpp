@@ -65,7 +65,7 @@ void oracle_brute_force(const float* vecs, const float* norms, uint32_t n, int d
     Data D = make_data(vecs, norms, n, d, ld, sim);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads > 0 ? nthreads : 1)
     for (int qi = 0; qi < nq; ++qi) {
-        Query q{queries + (size_t)qi * qld, sim == SIM_COSINE ? norm_ordered(queries + (size_t)qi * qld, d) : 0.0f};
+        Query q{queries + (size_t)qi * qld, sim != SIM_DOT ? norm_ordered(queries + (size_t)qi * qld, d) : 0.0f};
         auto r = brute_force_search(D, q, (size_t)k, min_score, alive_bits, n_paragraphs, first_vec, num_vec);
         out_count[qi] = (int)r.size();
         for (int j = 0; j < k; ++j) {
@@ -92,7 +92,7 @@ void oracle_hnsw_search(const float* vecs, const float* norms, uint32_t n, int d
 #ifdef _OPENMP
         t = omp_get_thread_num();
 #endif
-        Query q{queries + (size_t)qi * qld, sim == SIM_COSINE ? norm_ordered(queries + (size_t)qi * qld, d) : 0.0f};
+        Query q{queries + (size_t)qi * qld, sim != SIM_DOT ? norm_ordered(queries + (size_t)qi * qld, d) : 0.0f};
         NodeFilter f;
         f.filter_bits = filter_bits; f.paragraph_of = paragraph_of; f.with_duplicates = with_duplicates != 0; f.multi_vector = multi_vector != 0;
         auto r = hnsw_search(D, G, q, (size_t)k, ef, min_score, f, tls_scratch(), &cnts[t]);
@@ -116,7 +116,7 @@ int oracle_layer_search(const float* vecs, const float* norms, uint32_t n, int d
     Data D = make_data(vecs, norms, n, d, ld, sim);
     GraphView G = make_view(n, M, M0, level, 0, 0, const_cast<uint32_t*>(adj0), nullptr, upper_off, const_cast<uint32_t*>(adjU), nullptr);
     Scratch sc;
-    Query q{query, sim == SIM_COSINE ? norm_ordered(query, d) : 0.0f};
+    Query q{query, sim != SIM_DOT ? norm_ordered(query, d) : 0.0f};
     std::vector<uint32_t> e(eps, eps + n_eps);
     auto r = layer_search(D, G, q, layer, (size_t)k, e, sc, nullptr);
     for (size_t i = 0; i < r.size(); ++i) { out_ids[i] = r[i].id; out_scores[i] = r[i].score; }

@@ -32,7 +32,7 @@
 
 namespace nidx_oracle {
 
-enum Similarity : int { SIM_DOT = 0, SIM_COSINE = 1 };
+enum Similarity : int { SIM_DOT = 0, SIM_COSINE = 1, SIM_L2 = 2 };   // L2: an extension, the reference has none (config.rs:33-37)
 
 // Lane 0's value of the xor butterfly (v[l] += v[l ^ off] for off = 16, 8, 4, 2, 1).  Lane 0 only ever consumes lanes below
 // `off`, whose values are v[l] + v[l + off] with the operands in that order: the halving tree below is the same arithmetic
@@ -79,6 +79,7 @@ static inline float cosine_from_parts(float ab, float na, float nb) {
 
 static inline float similarity(int sim, const float* a, float na, const float* b, float nb, int d) {
     float ab = dot_ordered(a, b, d);
+    if (sim == SIM_L2) return 2.0f * ab - (na * na + nb * nb);   // -|a - b|^2 from the ordered dot and the norms (csrc/common.cuh l2_from_parts)
     return sim == SIM_COSINE ? cosine_from_parts(ab, na, nb) : ab;
 }
 

@@ -113,11 +113,11 @@ struct GraphView {
 
 struct Data {
     const float* vecs = nullptr;   // [n][ld]
-    const float* norms = nullptr;  // [n] norm_ordered, only read for cosine
+    const float* norms = nullptr;  // [n] norm_ordered, read for cosine and L2
     uint32_t n = 0;
     int d = 0, ld = 0, sim = SIM_DOT;
     const float* vec(uint32_t i) const { return vecs + (size_t)i * ld; }
-    float nrm(uint32_t i) const { return sim == SIM_COSINE ? norms[i] : 0.0f; }
+    float nrm(uint32_t i) const { return sim != SIM_DOT ? norms[i] : 0.0f; }
 };
 
 struct Scored {

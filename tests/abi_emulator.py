@@ -39,7 +39,7 @@ def _deref(byref_arg):
 
 class _Vec:
     def __init__(self, cfg, vecs, par_of):
-        self.d, self.sim = cfg.dimension, (O.SIM_COSINE if cfg.similarity == _lib.NIDX_SIM_COSINE else O.SIM_DOT)
+        self.d, self.sim = cfg.dimension, {_lib.NIDX_SIM_COSINE: O.SIM_COSINE, _lib.NIDX_SIM_DOT: O.SIM_DOT, _lib.NIDX_SIM_L2: O.SIM_L2}[cfg.similarity]
         self.multi, self.m, self.m0, self.efc, self.ef = bool(cfg.multi_vector), cfg.m, cfg.m0, cfg.ef_construction, cfg.ef_search
         self.v = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.d)
         self.n = len(self.v)
@@ -172,7 +172,87 @@ class EmulatedLib:
         s.g = O.hnsw_extend(s.v, g0, sim=s.sim, efC=s.efc, seed=_v(seed), max_batch=mb, nthreads=4)
         return 0
 
-    def nidx_vec_search(self, h, queries, nq, ldq, mem, params, out_ids, out_scores, out_counts, stream):
+    # ---- filters on the "device" (api.cu filter_formula_device restated with numpy) --------------------------------------------
+    def nidx_vec_set_inverted_index(self, h, which, n_keys, key_bytes, key_off, post_off, postings):
+        s, which, n = self._get(h), _v(which), _v(n_keys)
+        ko = _arr(key_off, np.uint64, n + 1) if n else np.zeros(1, np.uint64)
+        po = _arr(post_off, np.uint64, n + 1) if n else np.zeros(1, np.uint64)
+        kb = bytes(_arr(key_bytes, np.uint8, int(ko[n]))) if n and int(ko[n]) else b""
+        ps = _arr(postings, np.uint32, int(po[n])).copy() if n and int(po[n]) else np.zeros(0, np.uint32)
+        keys = [kb[int(ko[i]):int(ko[i + 1])] for i in range(n)]
+        if any(keys[i] >= keys[i + 1] for i in range(n - 1)):
+            return self._fail(-1, "inverted index keys must be strictly ascending")
+        if not hasattr(s, "inv"):
+            s.inv = {}
+        s.inv[which] = (keys, [ps[int(po[i]):int(po[i + 1])] for i in range(n)])
+        return 0
+
+    def _formula_bits(self, s, nodes, n_nodes):
+        """-> bool mask over paragraphs (before the alive intersection), or an error string."""
+        nodes = C.cast(nodes, C.POINTER(_lib.FilterNode)) if not isinstance(nodes, C.Array) else nodes
+        pos = [0]
+
+        def ev():
+            i = pos[0]
+            if i >= n_nodes:
+                raise ValueError("malformed filter formula")
+            nd = nodes[i]
+            pos[0] += 1
+            out = np.zeros(s.n_par, dtype=bool)
+            if nd.kind in (_lib.NIDX_F_LABEL, _lib.NIDX_F_KEYS):
+                keys, posts = getattr(s, "inv", {}).get(_lib.NIDX_INV_LABELS if nd.kind == _lib.NIDX_F_LABEL else _lib.NIDX_INV_FIELDS, ([], []))
+                for j in range(nd.n):
+                    qk = C.string_at(nd.keys[j], nd.key_len[j]) if nd.key_len[j] else b""
+                    for kk, pp in zip(keys, posts):
+                        if (kk.startswith(qk) if nd.kind == _lib.NIDX_F_LABEL else kk == qk):
+                            out[pp] = True
+                return out
+            if nd.n < 1:
+                raise ValueError("a compound clause needs operands")
+            acc = ev()
+            for _ in range(nd.n - 1):
+                b = ev()
+                acc = (acc | b) if nd.kind == _lib.NIDX_F_OR else (acc & b)
+            return ~acc if nd.kind == _lib.NIDX_F_NOT else acc
+
+        mask = ev()
+        if pos[0] != n_nodes:
+            raise ValueError("malformed filter formula")
+        return mask
+
+    @staticmethod
+    def _pack(mask):
+        words = np.zeros((len(mask) + 63) // 64 * 8, dtype=np.uint8)
+        pb = np.packbits(mask, bitorder="little")
+        words[: len(pb)] = pb
+        return words.view(np.uint64)
+
+    def nidx_vec_filter(self, h, nodes, n_nodes, out_bits, mem, out_matching, stream):
+        s = self._get(h)
+        try:
+            bits = self._pack(self._formula_bits(s, nodes, _v(n_nodes)))
+        except ValueError as e:
+            return self._fail(-1, str(e))
+        if s.alive is not None:
+            bits = bits & s.alive
+        ob = _arr(out_bits, np.uint64, len(bits))
+        if ob is not None:
+            ob[:] = bits
+        if out_matching is not None:
+            _deref(out_matching).value = int(sum(bin(int(w)).count("1") for w in bits))
+        return 0
+
+    def nidx_vec_search_formula(self, h, queries, nq, ldq, mem, params, nodes, n_nodes, out_ids, out_scores, out_counts, stream):
+        s = self._get(h)
+        if _deref(params).filter_bits:
+            return self._fail(-1, "give either filter_bits or a formula")
+        try:
+            bits = self._pack(self._formula_bits(s, nodes, _v(n_nodes)))
+        except ValueError as e:
+            return self._fail(-1, str(e))
+        return self.nidx_vec_search(h, queries, nq, ldq, mem, params, out_ids, out_scores, out_counts, stream, formula_bits=bits)
+
+    def nidx_vec_search(self, h, queries, nq, ldq, mem, params, out_ids, out_scores, out_counts, stream, formula_bits=None):
         s, nq, ldq, p = self._get(h), _v(nq), _v(ldq), _deref(params)
         if ldq < s.d:
             return self._fail(-1, f"query dimension {ldq} != index dimension {s.d} (VectorErr::InconsistentDimensions)")
@@ -180,14 +260,19 @@ class EmulatedLib:
         q = _arr(queries, np.float32, nq * ldq).reshape(nq, ldq)[:, : s.d].copy()
         ids, sc, cnt = _arr(out_ids, np.uint32, nq * k).reshape(nq, k), _arr(out_scores, np.float32, nq * k).reshape(nq, k), _arr(out_counts, np.int32, nq)
         words = (s.n_par + 63) // 64
-        bits, matching = s.alive, s.n_par                                   # api.cu: filter AND alive, matching as the caller states it
-        if p.filter_bits:
-            f = _arr(p.filter_bits, np.uint64, words)
+        bits = s.alive                                                      # api.cu: filter AND alive, matching as the caller states it
+        matching = s.n_par if s.alive is None else int(sum(bin(int(w)).count("1") for w in s.alive))
+        filtered = bool(p.filter_bits) or formula_bits is not None
+        if filtered:
+            f = formula_bits if formula_bits is not None else _arr(p.filter_bits, np.uint64, words)
             bits = f.copy() if s.alive is None else (f & s.alive)
-            matching = p.filter_matching or int(sum(bin(int(w)).count("1") for w in bits))
+            matching = (p.filter_matching if formula_bits is None else 0) or int(sum(bin(int(w)).count("1") for w in bits))
+        if matching == 0:                                                   # segment.rs:532-534
+            ids[:], sc[:], cnt[:] = NIL, 0, 0
+            return 0
         method = p.method
         if method == _lib.NIDX_METHOD_AUTO:
-            if s.g is None or (matching == 0 and p.filter_bits):
+            if s.g is None or (matching == 0 and filtered):
                 method = _lib.NIDX_METHOD_BRUTE
             else:
                 method = _lib.NIDX_METHOD_HNSW if O.use_hnsw(s.n_par, matching, k, M=s.m) else _lib.NIDX_METHOD_BRUTE

@@ -120,3 +120,26 @@ def test_auto_takes_the_quantised_walk_on_a_segment_with_codes():
     b_ids, _, _ = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
     recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(w_ids, b_ids)])
     assert recall >= 0.97, recall
+
+
+def test_vectors_quant_round_trip(tmp_path):
+    """vectors.quant (data_store/v2/quant_vector_store.rs:29-62): written with the segment, byte for byte the reference's records
+    (the oracle's encoder), and loaded as is by nidx_vec_open -- a segment written by the reference keeps its codes."""
+    n, d = 2000, 128
+    v = make_vectors(n, d, seed=71)
+    q = make_queries(v, 16)
+    seg = VectorSegment.create(v, d, similarity=_lib.NIDX_SIM_DOT, m=16, m0=32, ef_construction=64)
+    seg.build_hnsw(seed=2, max_batch=256)
+    seg.rabitq_encode()
+    seg.save(str(tmp_path))
+    raw = np.fromfile(tmp_path / "vectors.quant", dtype=np.uint8).reshape(n, d // 8 + 8)
+    assert np.array_equal(raw, O.rabitq_encode(v, nthreads=4))
+    want = seg.search(q, 10, method=_lib.NIDX_METHOD_HNSW_RABITQ)
+    # a "reference-written" directory: the codes come from the file, nothing is re-encoded
+    back = VectorSegment.open(str(tmp_path), d, similarity=_lib.NIDX_SIM_DOT, m=16, m0=32, ef_construction=64)
+    assert np.array_equal(back.rabitq_codes(), raw)
+    got = back.search(q, 10, method=_lib.NIDX_METHOD_AUTO)         # AUTO: codes present + graph => the quantised walk
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
+    (tmp_path / "vectors.quant").write_bytes(raw.tobytes()[:-3])
+    with pytest.raises(_lib.NidxError):
+        VectorSegment.open(str(tmp_path), d, similarity=_lib.NIDX_SIM_DOT, m=16, m0=32, ef_construction=64)

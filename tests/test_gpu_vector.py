@@ -381,3 +381,28 @@ def test_extend_when_a_new_node_raises_the_top_layer():
     bi, _, _ = seg.search(q, 10, method=_lib.NIDX_METHOD_BRUTE)
     hi, _, _ = seg.search(q, 10, ef=64, method=_lib.NIDX_METHOD_HNSW)
     assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(hi, bi)]) >= 0.97 and (hi < n0).any()
+
+
+def test_l2_similarity_extension():
+    """NIDX_SIM_L2 (north_star; the reference has none): -|q - v|^2 as a similarity.  Exact scan and HNSW walk equal the oracle's
+    restatement bit for bit; the ranking is the Euclidean nearest-neighbour ranking of a float64 brute force."""
+    n, d = 12000, 96
+    v = make_vectors(n, d, seed=31) * np.random.default_rng(5).uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    q = make_queries(v, 40) * 1.1
+    seg = VectorSegment.create(v, d, similarity=_lib.NIDX_SIM_L2, m=16, m0=32, ef_construction=100)
+    ids, sc, cnt = seg.search(q, 10, min_score=-1e30, method=_lib.NIDX_METHOD_BRUTE)
+    oi, os_, oc = O.brute_force(v, q, 10, sim=O.SIM_L2, min_score=-1e30, nthreads=8)
+    assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+    d2 = ((q[:, None, :].astype(np.float64) - v[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    exact = np.argsort(d2, axis=1)[:, :10]
+    assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(ids, exact)]) >= 0.99
+    assert np.allclose(-sc, np.take_along_axis(d2, ids.astype(np.int64), 1), rtol=1e-4, atol=1e-4)
+    seg.build_hnsw(seed=2, max_batch=512)
+    g = seg.get_graph()
+    og = O.Graph(n, 16, 32, g["level"])
+    og.adj0[:], og.adjU[:] = g["adj0"], g["adjU"][: og.adjU.shape[0]]
+    og.entry_node, og.entry_layer = g["entry_node"], g["entry_layer"]
+    hi, hs, hc = seg.search(q, 10, ef=64, min_score=-1e30, method=_lib.NIDX_METHOD_HNSW)
+    gi, gs, gc, _ = O.hnsw_search(v, og, q, 10, 64, sim=O.SIM_L2, min_score=-1e30, nthreads=8)
+    assert (hc == gc).all() and (hi == gi).all() and np.array_equal(hs, gs)
+    assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(hi, ids)]) >= 0.95
