@@ -39,6 +39,10 @@ def parse_args():
     ap.add_argument("--data", default="latent", choices=["latent", "gauss", "clustered"],
                     help="synthetic embeddings: 'latent' (default, DESIGN.md 5) = 16-d gaussian latent -> linear map + 15 %% noise; 'gauss' = BASELINE.md 3's "
                          "N(0,1) normalised; 'clustered' = BASELINE.md 3's 4 096 centres, points = normalise(centre + 0.1 * unit noise) (segment.rs:697-706)")
+    ap.add_argument("--hybrid", action="store_true",
+                    help="BASELINE configs[4]: after the vector measurement every rank also indexes --hybrid-docs / N documents (BM25, doc-partitioned, global "
+                         "statistics by all_reduce) and the line gains a `hybrid` block: sharded BM25 top-100 and vector + BM25 back to back per batch")
+    ap.add_argument("--hybrid-docs", type=int, default=5_000_000)
     ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (BASELINE configs 1 and 4 + the quantised walk at N = 1)")
     ap.add_argument("--latent", type=int, default=16)
     ap.add_argument("--noise", type=float, default=0.15)
@@ -256,6 +260,88 @@ def run_cpu_baseline(O, host_vecs, og, hq0, gpu_ids_first_batch, nq, k, ef, core
     rate1, _, _ = cpu_search_rate(O, host_vecs, og, hq0[:128], k, ef, norms, 1, native)      # one core, for the per-core figure
     return {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "sample": f"{ns} queries (the timed batches{', repeated' if reps > 1 else ''}), {dt:.1f} s",
             "native_isa": native, "ids_identical_to_gpu": same, "single_thread_qps": rate1}
+
+
+def run_hybrid(args, rank, world, local_rank, dev, comm, seg, queries, k, ef, multi):
+    """configs[4]: every rank holds one vector segment AND the postings of its own documents.  Per batch: sharded vector search
+    (search -> ncclAllGather -> Fssc merge) and sharded BM25 (local top-100 + Count -> ncclAllGather + ncclAllReduce -> merge), both
+    inside the C ABI on one stream.  Statistics (N, df, tokens) are those of the union of the parts (nidx_tantivy index_reader.rs:39-77)."""
+    import torch
+    import torch.distributed as dist
+
+    import bench_extra as BX
+    from nucliadb_b200 import _lib
+    from nucliadb_b200.dist import ShardComm
+    from nucliadb_b200.segment import TextSegment
+    from nucliadb_b200.text import fieldnorm_to_id
+
+    own_comm = comm is None
+    if own_comm:
+        comm = ShardComm(rank, world, local_rank, exchange=(lambda b: b) if not multi else None)
+    n_terms, nq, kt = 1_000_000, args.batch, 100
+    per = args.hybrid_docs // world
+    t0 = time.perf_counter()
+    c = BX.make_corpus(per, n_terms, dev, seed=7 + rank)
+    lut = np.asarray([fieldnorm_to_id(i) for i in range(int(c["lens"].max()) + 1)], dtype=np.uint8)
+    fieldnorm = lut[c["lens"]]
+    df = torch.from_numpy(np.diff(c["term_off"].astype(np.int64))).to(dev)
+    tot = torch.tensor([per, c["total_tokens"]], dtype=torch.int64, device=dev)
+    if multi:
+        dist.all_reduce(df)
+        dist.all_reduce(tot)
+    df_h = df.cpu().numpy().astype(np.uint64)
+    ts = TextSegment.create(per, n_terms, c["term_off"], c["post_doc"], c["post_tf"], fieldnorm, device=local_rank)
+    ts.set_stats(int(tot[0].item()), int(tot[1].item()), df_h)
+    t_setup = time.perf_counter() - t0
+    rng = np.random.default_rng(11)
+    band = np.nonzero((df_h >= 1_000) & (df_h <= 100_000))[0]
+    qs = [rng.choice(band, 50, replace=False).astype(np.uint32) for _ in range(nq)]
+    qoff = torch.tensor(np.concatenate([[0], np.cumsum([len(x) for x in qs])]), dtype=torch.int32, device=dev)
+    qt = torch.tensor(np.concatenate(qs).astype(np.int64), dtype=torch.int32, device=dev)
+    if multi:
+        dist.broadcast(qt, src=0)
+    t_out = (torch.empty((nq, kt), dtype=torch.int32, device=dev), torch.empty((nq, kt), dtype=torch.float32, device=dev),
+             torch.empty((nq, kt), dtype=torch.int32, device=dev), torch.empty((nq,), dtype=torch.int32, device=dev), torch.empty((nq,), dtype=torch.int64, device=dev))
+    v_out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+             torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq,), dtype=torch.int32, device=dev))
+
+    def text_step():
+        comm.search_text(ts, qt, qoff, kt, mode=_lib.NIDX_BM25_OR, use_tf=False, out=t_out)
+
+    def both_step(i):
+        comm.search_vectors(seg, queries[i % len(queries)], k, ef=ef, dedup=True, out=v_out)
+        text_step()
+
+    def timed_ms(fn, steps):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if multi:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    ms_text = timed_ms(lambda i: text_step(), args.steps)
+    ms_both = timed_ms(both_step, args.steps)
+    postings = float(sum(int(df_h[t]) for q in qs for t in q)) / nq
+    out = {"workload": f"hybrid: {world} x ({len(seg)} x {args.dim} vectors + {per} docs), 50-term OR queries top-{kt} + k-NN k={k} ef={ef}, batch {nq}",
+           "bm25_sharded": {"ms_per_step": ms_text, "queries_per_s": nq / (ms_text * 1e-3), "docs_total": per * world, "postings_per_query": postings,
+                            "note": "every query is scored on all parts; Count = ncclAllReduce, top-100 = ncclAllGather + merge (shard_merge.rs:227-231)"},
+           "vector_plus_bm25": {"ms_per_step": ms_both, "hybrid_queries_per_s": nq / (ms_both * 1e-3)},
+           "text_setup_seconds": t_setup}
+    ts.close()
+    if own_comm:
+        comm.close()
+    return out
 
 
 def main():
@@ -585,12 +671,18 @@ def main():
         hq0 = torch.cat(queries[args.warmup:]).cpu().numpy()   # the timed batches, in order
         cpu = run_cpu_baseline(O, host_vecs, og, hq0, ids_np, nq, k, ef, cores, args.cpu_seconds)
 
+    # ---- BASELINE configs[4]: hybrid vector + BM25 over the same ranks (doc-partitioned text index, NCCL merge inside the library) ----
+    hybrid = None
+    if args.hybrid and args.impl == "ours":
+        hybrid = run_hybrid(args, rank, world, local_rank, dev, comm, seg, queries, k, ef, multi)
+
     # ---- the other BASELINE configs, N = 1 only: exact scan (configs[0]), BM25 (configs[3]), the quantised walk ----
     extra = None
     if rank == 0 and not multi and not args.no_extra:
         try:
             import bench_extra as BX
 
+            host_vecs = None
             seg.close()                      # 33 GB of vectors + graph back to the allocator first
             del seg
             torch.cuda.empty_cache()
@@ -621,6 +713,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * (12 if use_lib else 8) + nq * 4, **e2e_mode},
             "gpu_launches": int(launches),
+            "hybrid": hybrid,
             "extra": extra,
             "visited_overflows": int(overflow),
             "clocks": clocks.summary(),

@@ -10,6 +10,7 @@ import pytest
 import abi_emulator
 import test_gpu_mirror
 import test_gpu_mirror_segment
+import test_gpu_binding
 import test_gpu_zz_open_dir
 from nucliadb_b200 import _lib
 
@@ -17,7 +18,7 @@ SKIP = {"test_segment_files_round_trip": "compares device-built files with the o
 
 
 def _cases():
-    for mod in (test_gpu_mirror, test_gpu_mirror_segment, test_gpu_zz_open_dir):
+    for mod in (test_gpu_mirror, test_gpu_mirror_segment, test_gpu_zz_open_dir, test_gpu_binding):
         for name, fn in inspect.getmembers(mod, inspect.isfunction):
             if name.startswith("test_") and fn.__module__ == mod.__name__ and name not in SKIP:
                 marks = getattr(fn, "pytestmark", [])
