@@ -106,6 +106,12 @@ int nidx_vec_build_hnsw(nidx_vec_segment* seg, uint64_t seed, int32_t max_batch,
  * exactly these.  Pure host function: needs no device. */
 int nidx_hnsw_levels(uint64_t n, int32_t m, uint64_t seed, uint8_t* out_level);
 
+/* utils::normalize_vector (nidx_vector/src/utils.rs:20-23) for n rows of d floats ([n][ld], in place): x / sqrt(fold(acc + x*x)),
+ * the fold sequential in f32 exactly as the reference's iterator (bit-identical results).  Used at index time when
+ * VectorConfig.normalize_vectors is set (indexer.rs:94-146) and on the query (searcher.rs:246-252).  mem = NIDX_MEM_HOST copies
+ * in and out and waits; NIDX_MEM_DEVICE works in place on `stream`. */
+int nidx_normalize_vectors(int32_t device, float* vectors, uint64_t n, int32_t d, int32_t ld, int mem, void* stream);
+
 /* The planner's cost model (use_hnsw, segment.rs:626-660): 1 if the HNSW walk is estimated cheaper than the exhaustive scan
  * for `matching_nodes` of `total_nodes` paragraphs passing the filter.  has_rabitq = the segment carries 1-bit codes.  m = the
  * graph's M (the reference's compile-time hnsw::M = 30).  Pure host function: needs no device.  nidx_vec_search applies it for

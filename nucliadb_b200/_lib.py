@@ -21,7 +21,7 @@ NIL = 0xFFFFFFFF
 SYMBOLS = [
     "nidx_last_error", "nidx_device_count", "nidx_launch_count",
     "nidx_vec_create", "nidx_vec_open", "nidx_vec_save", "nidx_vec_close", "nidx_vec_len", "nidx_vec_device_vectors",
-    "nidx_use_hnsw", "nidx_hnsw_levels", "nidx_vec_build_hnsw", "nidx_vec_extend_hnsw", "nidx_vec_graph_dims", "nidx_vec_set_graph", "nidx_vec_get_graph", "nidx_vec_set_alive",
+    "nidx_use_hnsw", "nidx_hnsw_levels", "nidx_normalize_vectors", "nidx_vec_build_hnsw", "nidx_vec_extend_hnsw", "nidx_vec_graph_dims", "nidx_vec_set_graph", "nidx_vec_get_graph", "nidx_vec_set_alive",
     "nidx_vec_set_inverted_index", "nidx_vec_filter", "nidx_vec_search_formula",
     "nidx_vec_search", "nidx_merge_topk", "nidx_vec_counters", "nidx_vec_counters_ex", "nidx_vec_last_kernel_ms",
     "nidx_vec_rabitq_encode", "nidx_vec_rabitq_codes", "nidx_vec_rabitq_estimate",

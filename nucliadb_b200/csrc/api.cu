@@ -377,6 +377,62 @@ int nidx_vec_create(const nidx_vec_config* cfg, const float* vectors, uint64_t n
     return 0;
 }
 
+// ---- utils::normalize_vector (nidx_vector/src/utils.rs:20-23) ----------------------------------------------
+// magnitude = sqrt(fold(0.0, |acc, x| acc + x.powi(2))) -- a SEQUENTIAL f32 fold (powi(2) = one rounded multiply, no FMA) --
+// then x / magnitude per element.  One warp per vector: the row is staged in shared memory with coalesced loads, lane 0 replays
+// the fold in the reference's order (bit-identical to it), all lanes divide.  A zero vector divides by zero like the reference
+// (NaN components).  Called at index time (indexer.rs:94-146) and per query (searcher.rs:246-252): negligible next to a search.
+constexpr int NRM_WARPS = 4;
+__global__ void __launch_bounds__(NRM_WARPS * 32) normalize_rows_kernel(float* __restrict__ v, uint64_t n, int d, int ld) {
+    extern __shared__ float nrm_row[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* row = nrm_row + (size_t)warp * d;
+    for (uint64_t i = (uint64_t)blockIdx.x * NRM_WARPS + warp; i < n; i += (uint64_t)gridDim.x * NRM_WARPS) {
+        float* src = v + i * (uint64_t)ld;
+        for (int j = lane; j < d; j += 32) row[j] = src[j];
+        __syncwarp();
+        float acc = 0.0f;
+        if (lane == 0)
+            for (int j = 0; j < d; ++j) acc = __fadd_rn(acc, __fmul_rn(row[j], row[j]));
+        float mag = __fsqrt_rn(__shfl_sync(0xFFFFFFFFu, acc, 0));
+        for (int j = lane; j < d; j += 32) src[j] = __fdiv_rn(row[j], mag);
+        __syncwarp();
+    }
+}
+
+int nidx_normalize_vectors(int32_t device, float* vectors, uint64_t n, int32_t d, int32_t ld, int mem, void* stream_) {
+    int dc = 0;
+    if (cudaGetDeviceCount(&dc) != cudaSuccess || dc == 0) return fail(NIDX_ENODEVICE, "no CUDA device (there is no CPU fallback)");
+    if (d <= 0 || ld < d || !vectors) return fail(NIDX_EINVAL, "normalize: d %d, ld %d", d, ld);
+    if ((size_t)d * 4 * NRM_WARPS > 200 * 1024) return fail(NIDX_EINVAL, "normalize: dimension %d too large", d);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    float* dv = vectors;
+    void* staged = nullptr;
+    size_t bytes = (size_t)n * ld * 4;
+    if (mem == NIDX_MEM_HOST) {
+        CU(cudaMalloc(&staged, bytes));
+        dv = static_cast<float*>(staged);
+        cudaError_t e = cudaMemcpyAsync(dv, vectors, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { cudaFree(staged); return fail(NIDX_ECUDA, "normalize: H2D failed: %s", cudaGetErrorString(e)); }
+    }
+    int sm = 0;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    size_t smem = (size_t)d * 4 * NRM_WARPS;
+    cudaFuncSetAttribute(normalize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    uint64_t want = (n + NRM_WARPS - 1) / NRM_WARPS;
+    int grid = (int)std::min<uint64_t>(want, (uint64_t)sm * 16);
+    normalize_rows_kernel<<<grid, NRM_WARPS * 32, smem, st>>>(dv, n, d, ld);
+    LAUNCHED();
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && staged) e = cudaMemcpyAsync(vectors, dv, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && staged) e = cudaStreamSynchronize(st);
+    if (staged) cudaFree(staged);
+    if (e != cudaSuccess) return fail(NIDX_ECUDA, "normalize failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 void nidx_vec_close(nidx_vec_segment* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);

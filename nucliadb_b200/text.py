@@ -29,7 +29,9 @@ _TOKEN = re.compile(r"[^\W_]+", re.UNICODE)
 
 
 def tokenize(text: str) -> list:
-    return [t.lower() for t in _TOKEN.findall(text) if len(t) <= 40]
+    """tantivy's "default" analyzer [recalled]: SimpleTokenizer (alphanumeric runs) -> RemoveLongFilter::limit(40), which keeps a
+    token iff `token.text.len() < 40` -- a length in UTF-8 BYTES, strictly below the limit -- -> LowerCaser."""
+    return [t.lower() for t in _TOKEN.findall(text) if len(t.encode("utf-8")) < 40]
 
 
 def fieldnorm_to_id(n: int) -> int:

@@ -276,8 +276,8 @@ class OpenSegment:
             first.append(len(vecs))
         arr = np.stack(vecs).astype(np.float32) if vecs else np.zeros((0, dim), dtype=np.float32)
         if config.normalize_vectors and len(arr):  # indexer.rs:94-146 normalises at index time (utils.rs:20-23)
-            mag = np.sqrt(np.add.reduce(arr.astype(np.float32) ** 2, axis=1, dtype=np.float32))
-            arr = (arr / mag[:, None]).astype(np.float32)
+            arr = np.ascontiguousarray(arr, dtype=np.float32)   # sequential f32 fold on the device, bit-identical to the reference's
+            check(L.nidx_normalize_vectors(C.c_int32(config.device), ptr(arr), C.c_uint64(len(arr)), C.c_int32(dim), C.c_int32(dim), _lib.NIDX_MEM_HOST, None))
         par = np.asarray(par_of, dtype=np.uint32)
         h = C.c_void_p()
         cfg = config._c()
@@ -491,10 +491,7 @@ class VectorSearcher:
         operator_and = request.filter_operator == FilterOperator.And
         query = np.asarray(request.vector, dtype=np.float32)
         if self.config.normalize_vectors and self.config.vector_cardinality != VectorCardinality.Multi:  # searcher.rs:246-252, utils.rs:20-23
-            mag = np.float32(0)
-            for x in query:
-                mag = np.float32(mag + np.float32(x) * np.float32(x))
-            query = (query / np.sqrt(mag)).astype(np.float32)
+            query = self._normalize(query)
         multi = self.config.vector_cardinality == VectorCardinality.Multi
         if (len(query) != self.config.dimension) if not multi else (len(query) % self.config.dimension != 0 or len(query) == 0):
             raise NidxError(-1, f"InconsistentDimensions: index_config {self.config.dimension}, vector {len(query)}")
@@ -523,7 +520,7 @@ class VectorSearcher:
         k = request.result_per_page
         qv = np.asarray(request.vector, dtype=np.float32).reshape(-1, d)
         if self.config.normalize_vectors:
-            qv = np.stack([self._normalize(v) for v in qv])
+            qv = self._normalize(qv)
         if k <= 0 or prefilter.kind == "none":
             return VectorSearchResponse([])
         first_k = max(k, 10)
@@ -551,12 +548,13 @@ class VectorSearcher:
         docs = [DocumentScored(seg.keys[p], sc, list(seg.labels[p]), seg.metadata[p]) for sc, seg, p in scored[:k]]
         return VectorSearchResponse(docs)
 
-    @staticmethod
-    def _normalize(v):
-        mag = np.float32(0)
-        for x in v:
-            mag = np.float32(mag + np.float32(x) * np.float32(x))
-        return (v / np.sqrt(mag)).astype(np.float32)
+    def _normalize(self, v):
+        """utils.rs:20-23 through the C ABI (nidx_normalize_vectors): one vector [d] or rows [n][d]."""
+        a = np.array(v, dtype=np.float32, ndmin=2)
+        if a.size:
+            check(_lib.require_device().nidx_normalize_vectors(C.c_int32(self.config.device), ptr(a), C.c_uint64(a.shape[0]), C.c_int32(a.shape[1]),
+                                                               C.c_int32(a.shape[1]), _lib.NIDX_MEM_HOST, None))
+        return a.reshape(np.shape(v))
 
     @staticmethod
     def _vector_bytes(seg: OpenSegment, addr: int) -> bytes:

@@ -94,6 +94,13 @@ class EmulatedLib:
     def nidx_use_hnsw(self, total, matching, k, rq, m):
         return int(O.use_hnsw(_v(total), _v(matching), _v(k), has_rabitq=bool(_v(rq)), M=_v(m)))
 
+    def nidx_normalize_vectors(self, device, vectors, n, d, ld, mem, stream):
+        n, d, ld = _v(n), _v(d), _v(ld)
+        a = np.ctypeslib.as_array(C.cast(vectors, C.POINTER(C.c_float)), shape=(n, ld))
+        for i in range(n):
+            a[i, :d] = O.normalize(a[i, :d].copy())
+        return 0
+
     # ---- vector segments -----------------------------------------------------------------------------------------------
     def nidx_vec_create(self, cfg, vectors, n, ld, mem, paragraph_of, out):
         cfg, n, ld = _deref(cfg), _v(n), _v(ld)

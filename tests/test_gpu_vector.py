@@ -406,3 +406,30 @@ def test_l2_similarity_extension():
     gi, gs, gc, _ = O.hnsw_search(v, og, q, 10, 64, sim=O.SIM_L2, min_score=-1e30, nthreads=8)
     assert (hc == gc).all() and (hi == gi).all() and np.array_equal(hs, gs)
     assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(hi, ids)]) >= 0.95
+
+
+@pytest.mark.gpu
+def test_normalize_vectors_matches_the_reference_fold():
+    """utils.rs:20-23 through nidx_normalize_vectors: sequential f32 fold, bit-identical to the oracle's restatement; host and
+    device buffers, a leading dimension larger than d, the reference's own known answers (utils.rs:140-155)."""
+    import ctypes as C
+
+    import torch
+
+    L = _lib.require_device()
+    rng = np.random.default_rng(5)
+    for n, d, ld in [(1, 4, 4), (37, 100, 100), (1000, 768, 768), (5, 3, 8)]:
+        a = (rng.standard_normal((n, ld)) * rng.uniform(0.01, 100)).astype(np.float32)
+        want = a.copy()
+        for i in range(n):
+            want[i, :d] = O.normalize(a[i, :d].copy())
+        h = a.copy()
+        _lib.check(L.nidx_normalize_vectors(0, _lib.ptr(h), C.c_uint64(n), d, ld, _lib.NIDX_MEM_HOST, None))
+        assert h.tobytes() == want.tobytes()
+        t = torch.from_numpy(a.copy()).cuda()
+        _lib.check(L.nidx_normalize_vectors(0, _lib.ptr(t), C.c_uint64(n), d, ld, _lib.NIDX_MEM_DEVICE, None))
+        torch.cuda.synchronize()
+        assert t.cpu().numpy().tobytes() == want.tobytes()
+    v = np.asarray([[3.0, 0.0, 4.0, 0.0]], dtype=np.float32)
+    _lib.check(L.nidx_normalize_vectors(0, _lib.ptr(v), C.c_uint64(1), 4, 4, _lib.NIDX_MEM_HOST, None))
+    assert v[0].tolist() == [np.float32(3.0) / np.float32(5.0), 0.0, np.float32(4.0) / np.float32(5.0), 0.0]

@@ -68,6 +68,8 @@ def test_fieldnorm_code_matches_oracle_table():
 def test_tokenizer_is_lowercase_alnum():
     assert T.tokenize("Hello, World! it's 42") == ["hello", "world", "it", "s", "42"]
     assert T.tokenize("x" * 41) == []
+    assert T.tokenize("x" * 40) == [] and T.tokenize("x" * 39) == ["x" * 39]      # RemoveLongFilter: len < 40 ...
+    assert T.tokenize("é" * 20) == [] and T.tokenize("é" * 19) == ["é" * 19]      # ... counted in UTF-8 bytes
 
 
 # ---- paragraphs.bin / paragraphs.pos (data_store/v2/paragraph_store.rs; bincode 2 standard config, utils.rs:25-28) ---------
