@@ -303,6 +303,59 @@ int nidx_txt_search_sharded(nidx_shard_comm* comm, nidx_txt_segment* seg, const 
                             const nidx_txt_search_params* p, uint32_t* out_docs, float* out_scores, int32_t* out_part, int32_t* out_counts, uint64_t* out_total,
                             void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * One shard search as ONE device-side plan + rank fusion on the device
+ * (reference: run_index_searches, nidx/src/searcher/shard_search.rs:176-241 -- the paragraph, document and vector searches of a
+ *  request run on scoped threads; the ranked lists are fused afterwards in Python,
+ *  nucliadb/src/nucliadb/search/search/rank_fusion.py:78-186)
+ * ------------------------------------------------------------------------------------------ */
+/* Caller keys of a text segment's documents (for the paragraph index: the paragraph id, as a 64-bit hash or table index -- the
+ * same key space as nidx_vec_set_paragraph_keys), used to match keyword and semantic results.  NULL = the document number. */
+int nidx_txt_set_doc_keys(nidx_txt_segment* seg, const uint64_t* keys);
+
+typedef struct nidx_rrf_source {
+    const uint64_t* keys;     /* [nq][k] item keys, best first (every source sorted by its score, descending); ~0 = no item */
+    const float* scores;      /* [nq][k] the source's scores: reported as they are when only one source has results (rank_fusion.py:86-89) */
+    const int32_t* counts;    /* [nq] valid items per query; NULL = k minus trailing ~0 keys */
+    int32_t k;
+    double weight;            /* the retriever's boost w(r) (rank_fusion.py:133-141) */
+} nidx_rrf_source;
+
+/* ReciprocalRankFusion.fuse (rank_fusion.py:78-96, 143-186) for nq queries: score(d) = sum over the sources, in the order given, of
+ * 1 / (k + rank) * weight in IEEE double arithmetic (bit-identical to the reference's Python floats); one output item per key (the
+ * first occurrence), sorted by score descending, ties in first-insertion order (Python's stable sort).  Rows of out_* are
+ * sum(k_i) long: out_refs = first occurrence's source << 28 | mask of contributing sources << 24 | its position in that source;
+ * out_counts[nq] = number of fused items.  At most 4 sources. */
+int nidx_rank_fusion_rrf(int32_t device, const nidx_rrf_source* sources, int32_t n_sources, int32_t nq, double k, int mem, uint64_t* out_keys,
+                         double* out_scores, uint32_t* out_refs, int32_t* out_counts, void* stream);
+
+typedef struct nidx_shard_search_request {
+    int32_t nq;
+    /* vectors_request (shard_search.rs:211-213): vec == NULL = not requested */
+    nidx_vec_segment* vec; const float* queries; int32_t ldq; const nidx_vec_search_params* vec_params;
+    const nidx_filter_node* formula; int32_t n_formula;     /* optional filter formula evaluated on the device (nidx_vec_search_formula) */
+    /* paragraphs_request (shard_search.rs:189-191): the keyword search, BM25 over the paragraph index */
+    nidx_txt_segment* par; const uint32_t* par_terms; const uint32_t* par_off; const nidx_txt_search_params* par_params;
+    /* texts_request (shard_search.rs:185-187): BM25 over the document (field) index */
+    nidx_txt_segment* doc; const uint32_t* doc_terms; const uint32_t* doc_off; const nidx_txt_search_params* doc_params;
+    /* rank fusion of the paragraph (keyword) and vector (semantic) lists; rrf_k <= 0: none */
+    double rrf_k, weight_keyword, weight_semantic;
+    int32_t semantic_first;   /* order of the sources (the reference iterates a dict: insertion order decides ties and which item object survives) */
+} nidx_shard_search_request;
+
+typedef struct nidx_shard_search_response {
+    uint32_t* vec_ids; float* vec_scores; int32_t* vec_counts;                          /* [nq][vec_params->k] as nidx_vec_search */
+    uint32_t* par_docs; float* par_scores; int32_t* par_counts; uint64_t* par_total;    /* [nq][par_params->k] as nidx_txt_search */
+    uint32_t* doc_docs; float* doc_scores; int32_t* doc_counts; uint64_t* doc_total;    /* [nq][doc_params->k] */
+    uint64_t* fused_keys; double* fused_scores; uint32_t* fused_refs; int32_t* fused_counts;   /* [nq][kv + kp] as nidx_rank_fusion_rrf */
+} nidx_shard_search_response;
+
+/* run_index_searches for a batch of nq requests against one shard's indexes: the requested searches run concurrently on side
+ * streams forked from `stream`, are joined back, and (rrf_k > 0, vector and paragraph requests present) the two ranked lists
+ * are fused on the device -- keys through nidx_vec_set_paragraph_keys / nidx_txt_set_doc_keys.  `mem` applies to all inputs
+ * and outputs; with host buffers the call returns when the results are in them (one synchronisation at the end). */
+int nidx_shard_search(const nidx_shard_search_request* req, nidx_shard_search_response* resp, int mem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ SYMBOLS = [
     "nidx_vec_rabitq_encode", "nidx_vec_rabitq_codes", "nidx_vec_rabitq_estimate",
     "nidx_txt_create", "nidx_txt_set_stats", "nidx_txt_set_alive", "nidx_txt_close", "nidx_txt_search", "nidx_txt_last_kernel_ms",
     "nidx_shard_unique_id", "nidx_shard_init", "nidx_shard_destroy", "nidx_vec_set_paragraph_keys", "nidx_vec_search_sharded", "nidx_txt_search_sharded",
+    "nidx_txt_set_doc_keys", "nidx_rank_fusion_rrf", "nidx_shard_search",
 ]
 
 
@@ -59,6 +60,24 @@ NIDX_F_LABEL, NIDX_F_KEYS, NIDX_F_AND, NIDX_F_OR, NIDX_F_NOT = 0, 1, 2, 3, 4
 class TxtSearchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("mode", C.c_int32), ("use_tf", C.c_int32), ("min_score", C.c_float), ("after_mode", C.c_int32),
                 ("after_score", C.c_float), ("after_docaddr", C.c_uint64), ("docaddr_base", C.c_uint64)]
+
+
+class RrfSource(C.Structure):
+    _fields_ = [("keys", C.c_void_p), ("scores", C.c_void_p), ("counts", C.c_void_p), ("k", C.c_int32), ("weight", C.c_double)]
+
+
+class ShardSearchRequest(C.Structure):
+    _fields_ = [("nq", C.c_int32),
+                ("vec", C.c_void_p), ("queries", C.c_void_p), ("ldq", C.c_int32), ("vec_params", C.POINTER(VecSearchParams)),
+                ("formula", C.POINTER(FilterNode)), ("n_formula", C.c_int32),
+                ("par", C.c_void_p), ("par_terms", C.c_void_p), ("par_off", C.c_void_p), ("par_params", C.POINTER(TxtSearchParams)),
+                ("doc", C.c_void_p), ("doc_terms", C.c_void_p), ("doc_off", C.c_void_p), ("doc_params", C.POINTER(TxtSearchParams)),
+                ("rrf_k", C.c_double), ("weight_keyword", C.c_double), ("weight_semantic", C.c_double), ("semantic_first", C.c_int32)]
+
+
+class ShardSearchResponse(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("vec_ids", "vec_scores", "vec_counts", "par_docs", "par_scores", "par_counts", "par_total",
+                                           "doc_docs", "doc_scores", "doc_counts", "doc_total", "fused_keys", "fused_scores", "fused_refs", "fused_counts")]
 
 
 _lib = None

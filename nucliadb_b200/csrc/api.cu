@@ -20,6 +20,7 @@
 #include "hnsw_search.cuh"
 #include "hnsw_rabitq.cuh"
 #include "rabitq.cuh"
+#include "rank_fusion.cuh"
 #include "scan.cu"
 #include "scan_tc.cuh"
 #include "scan_tc2.cuh"
@@ -677,6 +678,29 @@ static hs_kernel_t pick_search_kernel(int ld) {
     return hnsw_search_kernel<0>;
 }
 
+// the 4-warp shape (two rows per warp in flight, 7 CTAs per SM): see hnsw_search_kernel
+static hs_kernel_t pick_search_kernel_w4(int ld) {
+    if (ld % 128 == 0) switch (ld / 128) {
+        case 1: return hnsw_search_kernel<1, 4, true>;
+        case 2: return hnsw_search_kernel<2, 4, true>;
+        case 3: return hnsw_search_kernel<3, 4, true>;
+        case 4: return hnsw_search_kernel<4, 4, true>;
+        case 6: return hnsw_search_kernel<6, 4, true>;
+        case 8: return hnsw_search_kernel<8, 4, true>;
+        default: break;
+    }
+    return nullptr;
+}
+
+static hs_kernel_t pick_search_kernel_w8pair(int ld) {
+    if (ld % 128 == 0) switch (ld / 128) {
+        case 3: return hnsw_search_kernel<3, 8, true>;
+        case 6: return hnsw_search_kernel<6, 8, true>;
+        default: break;
+    }
+    return nullptr;
+}
+
 static hs_kernel_t pick_rabitq_walk_kernel(int ld) {
     if (ld % 128 == 0) switch (ld / 128) {
         case 2: return hnsw_rabitq_kernel<2>;
@@ -1162,12 +1186,29 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
         CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
         hs_kernel_t kern = pick_search_kernel(s->ld);
+        int threads = HS_THREADS;
+        // Shape: 8 warps per query, 4 CTAs per SM -- or 4 warps with two rows in flight each, 7 CTAs per SM, when that lets the
+        // whole batch run as one wave (NIDX_B200_HS_W=4 / 8 forces a shape; the experiment's visited table is hs_w4_bits slots).
+        {
+            const char* e1 = getenv("NIDX_B200_HS_W");
+            const char* e2 = getenv("NIDX_B200_HS_W4_BITS");
+            const int force_w = e1 ? atoi(e1) : 0, w4_bits = e2 ? atoi(e2) : 0;
+            hs_kernel_t k4 = pick_search_kernel_w4(s->ld);
+            const char* e3 = getenv("NIDX_B200_HS_PAIR");
+            hs_kernel_t k8p = pick_search_kernel_w8pair(s->ld);
+            if (k8p && force_w != 4 && e3 && atoi(e3) == 1) kern = k8p;
+            if (k4 && force_w == 4) {
+                int hb = w4_bits > 0 ? w4_bits : hash_bits;
+                size_t smem4 = hs_smem_bytes(s->ld, list_cap, hb);
+                kern = k4; threads = 128; smem = smem4; a.hash_bits = hb;
+            }
+        }
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HS_THREADS, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         int grid = std::min(nq, std::max(1, occ) * s->sm_count);
         CU(cudaEventRecord(s->ev_k0, stream));
-        kern<<<grid, HS_THREADS, smem, stream>>>(V, s->gdev(), a);
+        kern<<<grid, threads, smem, stream>>>(V, s->gdev(), a);
         CU(cudaEventRecord(s->ev_k1, stream));
         LAUNCHED();
         CU(cudaGetLastError());
@@ -1665,6 +1706,7 @@ struct nidx_txt_segment {
     float* d_weight = nullptr;   // [n_terms]
     float* d_norm_cache = nullptr;  // [256]
     unsigned int* d_error = nullptr;
+    uint64_t* d_doc_keys = nullptr;   // [n_docs] caller keys of the documents (paragraph ids) for rank fusion (nidx_txt_set_doc_keys)
     std::vector<uint64_t> own_df;
     uint64_t own_tokens = 0;
     float max_weight = 0.0f;
@@ -1789,7 +1831,7 @@ void nidx_txt_close(nidx_txt_segment* t) {
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
     cudaFree(t->d_term_off); cudaFree(t->d_post); cudaFree(t->d_skip_row); cudaFree(t->d_skip); cudaFree(t->d_alive); cudaFree(t->d_weight);
-    cudaFree(t->d_norm_cache); cudaFree(t->d_error);
+    cudaFree(t->d_norm_cache); cudaFree(t->d_error); cudaFree(t->d_doc_keys);
     if (t->ev_k0) cudaEventDestroy(t->ev_k0);
     if (t->ev_k1) cudaEventDestroy(t->ev_k1);
     delete t;
@@ -2058,6 +2100,218 @@ int nidx_txt_search_sharded(nidx_shard_comm* c, nidx_txt_segment* seg, const uin
     if (r) return r;
     if (host) {
         if (out_total) CU(cudaMemcpyAsync(out_total, d_total, (size_t)nq * 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+// ---- rank fusion + the fused shard search --------------------------------------------------------------
+int nidx_txt_set_doc_keys(nidx_txt_segment* t, const uint64_t* keys) {
+    if (!t) return fail(NIDX_EINVAL, "null segment");
+    CU(cudaSetDevice(t->device));
+    if (!keys) { cudaFree(t->d_doc_keys); t->d_doc_keys = nullptr; return 0; }
+    if (!t->d_doc_keys) CU(cudaMalloc(&t->d_doc_keys, std::max<size_t>(t->n_docs, 1) * 8));
+    CU(cudaMemcpy(t->d_doc_keys, keys, (size_t)t->n_docs * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // extern "C"
+
+static WorkspacePool* plan_pool(int device) {
+    static std::mutex mu;
+    static WorkspacePool* pools[64] = {nullptr};
+    std::lock_guard<std::mutex> g(mu);
+    if (device < 0 || device >= 64) return nullptr;
+    if (!pools[device]) pools[device] = new WorkspacePool();
+    return pools[device];
+}
+
+// sources already on the device; outputs on the device
+static int rrf_launch(const RrfSourceDev* src, int n_sources, int nq, double k, uint64_t* out_keys, double* out_scores, uint32_t* out_refs, int32_t* out_counts,
+                      cudaStream_t stream) {
+    RrfArgs a;
+    memset(&a, 0, sizeof(a));
+    int cap = 0;
+    for (int i = 0; i < n_sources; ++i) { a.src[i] = src[i]; cap += src[i].k; }
+    a.n_sources = n_sources; a.nq = nq; a.cap = cap; a.k = k;
+    a.out_keys = out_keys; a.out_scores = out_scores; a.out_refs = out_refs; a.out_counts = out_counts;
+    size_t smem = rf_smem_bytes(cap);
+    if (smem > 200 * 1024) return fail(NIDX_EINVAL, "rank fusion of %d items per query needs %zu bytes of shared memory: too many", cap, smem);
+    CU(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rrf_fuse_kernel<<<nq, RF_THREADS, smem, stream>>>(a);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// side streams of the fused shard search: one set per host thread and device (the reference runs the index searches of one request on
+// scoped threads, shard_search.rs:215-239; here they are streams forked from, and joined back into, the caller's stream)
+struct PlanStreams {
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+    int device = -1;
+    int init(int dev) {
+        if (device == dev) return 0;
+        if (device >= 0) return fail(NIDX_EINVAL, "a host thread uses nidx_shard_search on one device only (first %d, now %d)", device, dev);
+        for (int i = 0; i < 3; ++i) {
+            CU(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        device = dev;
+        return 0;
+    }
+};
+static thread_local PlanStreams g_plan_streams;
+
+extern "C" {
+
+int nidx_rank_fusion_rrf(int32_t device, const nidx_rrf_source* sources, int32_t n_sources, int32_t nq, double k, int mem, uint64_t* out_keys,
+                         double* out_scores, uint32_t* out_refs, int32_t* out_counts, void* stream_) {
+    int r = check_device(device);
+    if (r) return r;
+    if (!sources || n_sources <= 0 || n_sources > RF_MAX_SOURCES) return fail(NIDX_EINVAL, "rank fusion takes 1..%d sources", RF_MAX_SOURCES);
+    if (!out_keys || !out_scores || !out_refs || !out_counts) return fail(NIDX_EINVAL, "null output");
+    if (nq <= 0) return 0;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    bool host = mem == NIDX_MEM_HOST;
+    int cap = 0;
+    for (int i = 0; i < n_sources; ++i) {
+        if (sources[i].k <= 0 || !sources[i].keys || !sources[i].scores) return fail(NIDX_EINVAL, "rank fusion source %d: keys, scores and k > 0 are required", i);
+        if (sources[i].k >= (1 << 24)) return fail(NIDX_EINVAL, "rank fusion source %d: k too large", i);
+        cap += sources[i].k;
+    }
+    RrfSourceDev dev[RF_MAX_SOURCES];
+    WorkspacePool* pool = plan_pool(device);
+    if (!pool) return fail(NIDX_EINVAL, "device %d", device);
+    WsGuard g(*pool, stream);
+    Workspace& w = *g.w;
+    uint64_t* d_keys = out_keys; double* d_sc = out_scores; uint32_t* d_refs = out_refs; int32_t* d_cnt = out_counts;
+    if (host) {
+        size_t in_bytes = 0;
+        auto al16 = [](size_t b) { return (b + 15) / 16 * 16; };
+        for (int i = 0; i < n_sources; ++i) in_bytes += al16((size_t)nq * sources[i].k * 8) + al16((size_t)nq * sources[i].k * 4) + al16((size_t)nq * 4);
+        ENSURE(w.queries, in_bytes);
+        ENSURE(w.scores, (size_t)nq * cap * 20 + (size_t)nq * 4 + 128);
+        unsigned char* p = w.queries.as<unsigned char>();
+        for (int i = 0; i < n_sources; ++i) {
+            size_t nk = (size_t)nq * sources[i].k;
+            uint64_t* dk = reinterpret_cast<uint64_t*>(p); p += al16(nk * 8);
+            float* ds = reinterpret_cast<float*>(p); p += al16(nk * 4);
+            int32_t* dc = reinterpret_cast<int32_t*>(p); p += al16((size_t)nq * 4);
+            CU(cudaMemcpyAsync(dk, sources[i].keys, nk * 8, cudaMemcpyHostToDevice, stream));
+            CU(cudaMemcpyAsync(ds, sources[i].scores, nk * 4, cudaMemcpyHostToDevice, stream));
+            if (sources[i].counts) CU(cudaMemcpyAsync(dc, sources[i].counts, (size_t)nq * 4, cudaMemcpyHostToDevice, stream));
+            dev[i] = RrfSourceDev{dk, ds, sources[i].counts ? dc : nullptr, sources[i].k, sources[i].weight};
+        }
+        unsigned char* o = w.scores.as<unsigned char>();
+        d_keys = reinterpret_cast<uint64_t*>(o); o += (size_t)nq * cap * 8;
+        d_sc = reinterpret_cast<double*>(o); o += (size_t)nq * cap * 8;
+        d_refs = reinterpret_cast<uint32_t*>(o); o += al16((size_t)nq * cap * 4);
+        d_cnt = reinterpret_cast<int32_t*>(o);
+    } else {
+        for (int i = 0; i < n_sources; ++i) dev[i] = RrfSourceDev{sources[i].keys, sources[i].scores, sources[i].counts, sources[i].k, sources[i].weight};
+    }
+    r = rrf_launch(dev, n_sources, nq, k, d_keys, d_sc, d_refs, d_cnt, stream);
+    if (r) return r;
+    if (host) {
+        CU(cudaMemcpyAsync(out_keys, d_keys, (size_t)nq * cap * 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_scores, d_sc, (size_t)nq * cap * 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_refs, d_refs, (size_t)nq * cap * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(out_counts, d_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+int nidx_shard_search(const nidx_shard_search_request* rq, nidx_shard_search_response* rs, int mem, void* stream_) {
+    if (!rq || !rs) return fail(NIDX_EINVAL, "null argument");
+    const int nq = rq->nq;
+    if (nq <= 0) return 0;
+    if (!rq->vec && !rq->par && !rq->doc) return fail(NIDX_EINVAL, "shard search without any index request");
+    int device = rq->vec ? rq->vec->cfg.device : (rq->par ? rq->par->device : rq->doc->device);
+    if ((rq->vec && rq->vec->cfg.device != device) || (rq->par && rq->par->device != device) || (rq->doc && rq->doc->device != device))
+        return fail(NIDX_EINVAL, "the indexes of one shard search must live on one device");
+    if (rq->vec && (!rq->vec_params || !rs->vec_ids || !rs->vec_scores || !rs->vec_counts)) return fail(NIDX_EINVAL, "vector request: params and outputs are required");
+    if (rq->par && (!rq->par_params || !rs->par_docs || !rs->par_scores || !rs->par_counts)) return fail(NIDX_EINVAL, "paragraph request: params and outputs are required");
+    if (rq->doc && (!rq->doc_params || !rs->doc_docs || !rs->doc_scores || !rs->doc_counts)) return fail(NIDX_EINVAL, "document request: params and outputs are required");
+    const bool fuse = rq->rrf_k > 0.0 && rq->vec && rq->par;
+    if (fuse && (!rs->fused_keys || !rs->fused_scores || !rs->fused_refs || !rs->fused_counts)) return fail(NIDX_EINVAL, "rank fusion: outputs are required");
+    int r = check_device(device);
+    if (r) return r;
+    CU(cudaSetDevice(device));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const bool host = mem == NIDX_MEM_HOST;
+    PlanStreams& ps = g_plan_streams;
+    r = ps.init(device);
+    if (r) return r;
+    const int kv = rq->vec ? rq->vec_params->k : 0, kp = rq->par ? rq->par_params->k : 0, kd = rq->doc ? rq->doc_params->k : 0;
+    if ((rq->vec && kv <= 0) || (rq->par && kp <= 0) || (rq->doc && kd <= 0)) return fail(NIDX_EINVAL, "k must be positive");
+    WorkspacePool* pool = plan_pool(device);
+    WsGuard g(*pool, stream);
+    Workspace& w = *g.w;
+    // device-side results (the callers' buffers, or staging when they are host buffers) + fusion scratch
+    size_t nv = (size_t)nq * kv, np = (size_t)nq * kp, nd = (size_t)nq * kd, nf = (size_t)nq * (kv + kp), cw = ((size_t)nq * 4 + 15) / 16 * 16;
+    size_t stage_bytes = host ? nv * 8 + np * 8 + nd * 8 + 3 * cw + 2 * (size_t)nq * 8 + nf * 20 + cw : 0;
+    size_t key_bytes = fuse ? (nv + np) * 8 : 0;
+    ENSURE(w.scores, stage_bytes + key_bytes + 512);
+    unsigned char* p = w.scores.as<unsigned char>();
+    auto take = [&](size_t bytes) { unsigned char* q = p; p += (bytes + 15) / 16 * 16; return q; };
+    uint32_t *d_vid = rs->vec_ids, *d_pdoc = rs->par_docs, *d_ddoc = rs->doc_docs, *d_frf = rs->fused_refs;
+    float *d_vsc = rs->vec_scores, *d_psc = rs->par_scores, *d_dsc = rs->doc_scores;
+    int32_t *d_vcnt = rs->vec_counts, *d_pcnt = rs->par_counts, *d_dcnt = rs->doc_counts, *d_fcnt = rs->fused_counts;
+    uint64_t *d_ptot = rs->par_total, *d_dtot = rs->doc_total, *d_fkey = rs->fused_keys;
+    double* d_fsc = rs->fused_scores;
+    if (host) {
+        if (rq->vec) { d_vid = (uint32_t*)take(nv * 4); d_vsc = (float*)take(nv * 4); d_vcnt = (int32_t*)take(cw); }
+        if (rq->par) { d_pdoc = (uint32_t*)take(np * 4); d_psc = (float*)take(np * 4); d_pcnt = (int32_t*)take(cw); d_ptot = (uint64_t*)take((size_t)nq * 8); }
+        if (rq->doc) { d_ddoc = (uint32_t*)take(nd * 4); d_dsc = (float*)take(nd * 4); d_dcnt = (int32_t*)take(cw); d_dtot = (uint64_t*)take((size_t)nq * 8); }
+        if (fuse) { d_fkey = (uint64_t*)take(nf * 8); d_fsc = (double*)take(nf * 8); d_frf = (uint32_t*)take(nf * 4); d_fcnt = (int32_t*)take(cw); }
+    }
+    uint64_t *d_vkey = nullptr, *d_pkey = nullptr;
+    if (fuse) { d_vkey = (uint64_t*)take(nv * 8); d_pkey = (uint64_t*)take(np * 8); }
+
+    // fork: the three index searches run on their own streams, each ordered after whatever the caller enqueued before this call
+    CU(cudaEventRecord(ps.fork, stream));
+    for (int i = 0; i < 3; ++i) CU(cudaStreamWaitEvent(ps.s[i], ps.fork, 0));
+    // (text searches first: with host queries they enqueue without waiting; the vector search may wait for a filter count)
+    if (rq->par) {
+        r = txt_search_impl(rq->par, rq->par_terms, rq->par_off, nq, host, false, rq->par_params, d_pdoc, d_psc, d_pcnt, d_ptot, ps.s[1]);
+        if (r) return r;
+        CU(cudaEventRecord(ps.join[1], ps.s[1]));
+        CU(cudaStreamWaitEvent(stream, ps.join[1], 0));
+    }
+    if (rq->doc) {
+        r = txt_search_impl(rq->doc, rq->doc_terms, rq->doc_off, nq, host, false, rq->doc_params, d_ddoc, d_dsc, d_dcnt, d_dtot, ps.s[2]);
+        if (r) return r;
+        CU(cudaEventRecord(ps.join[2], ps.s[2]));
+        CU(cudaStreamWaitEvent(stream, ps.join[2], 0));
+    }
+    if (rq->vec) {
+        r = vec_search_impl(rq->vec, rq->queries, nq, rq->ldq, host, false, rq->vec_params, d_vid, d_vsc, d_vcnt, ps.s[0], rq->formula, rq->n_formula);
+        if (r) return r;
+        CU(cudaEventRecord(ps.join[0], ps.s[0]));
+        CU(cudaStreamWaitEvent(stream, ps.join[0], 0));
+    }
+    // join + rank fusion of the paragraph (keyword) and vector (semantic) results on the caller's stream
+    if (fuse) {
+        ids_to_keys_kernel<<<std::min<size_t>((nv + 255) / 256, 1024), 256, 0, stream>>>(d_vid, nv, rq->vec->d_par_of, rq->vec->d_par_keys, d_vkey);
+        LAUNCHED();
+        ids_to_keys_kernel<<<std::min<size_t>((np + 255) / 256, 1024), 256, 0, stream>>>(d_pdoc, np, nullptr, rq->par->d_doc_keys, d_pkey);
+        LAUNCHED();
+        RrfSourceDev src[2];
+        RrfSourceDev kw{d_pkey, d_psc, d_pcnt, kp, rq->weight_keyword}, sem{d_vkey, d_vsc, d_vcnt, kv, rq->weight_semantic};
+        src[0] = rq->semantic_first ? sem : kw;
+        src[1] = rq->semantic_first ? kw : sem;
+        r = rrf_launch(src, 2, nq, rq->rrf_k, d_fkey, d_fsc, d_frf, d_fcnt, stream);
+        if (r) return r;
+    }
+    if (host) {
+        auto back = [&](void* dst, const void* src, size_t bytes) { return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream) : cudaSuccess; };
+        if (rq->vec) { CU(back(rs->vec_ids, d_vid, nv * 4)); CU(back(rs->vec_scores, d_vsc, nv * 4)); CU(back(rs->vec_counts, d_vcnt, (size_t)nq * 4)); }
+        if (rq->par) { CU(back(rs->par_docs, d_pdoc, np * 4)); CU(back(rs->par_scores, d_psc, np * 4)); CU(back(rs->par_counts, d_pcnt, (size_t)nq * 4)); CU(back(rs->par_total, d_ptot, (size_t)nq * 8)); }
+        if (rq->doc) { CU(back(rs->doc_docs, d_ddoc, nd * 4)); CU(back(rs->doc_scores, d_dsc, nd * 4)); CU(back(rs->doc_counts, d_dcnt, (size_t)nq * 4)); CU(back(rs->doc_total, d_dtot, (size_t)nq * 8)); }
+        if (fuse) { CU(back(rs->fused_keys, d_fkey, nf * 8)); CU(back(rs->fused_scores, d_fsc, nf * 8)); CU(back(rs->fused_refs, d_frf, nf * 4)); CU(back(rs->fused_counts, d_fcnt, (size_t)nq * 4)); }
         CU(cudaStreamSynchronize(stream));
     }
     return 0;

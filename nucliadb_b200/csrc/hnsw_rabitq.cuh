@@ -41,28 +41,9 @@ struct RqCtx {
     unsigned long long n_quant, n_rerank;
 };
 
-// rabitq.rs:166-218 for the code at `code` (16-byte aligned, stride bytes, zero padded): (estimate, error bound)
-__device__ __forceinline__ void rq_estimate(const RqCtx& r, const unsigned char* __restrict__ code, int stride, float& estimate, float& error) {
-    const uint4* c4 = reinterpret_cast<const uint4*>(code);
-    uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, dqo_bits = 0, sum_bits = 0;
-    int nchunks = stride >> 4;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        uint4 w = __ldg(c4 + ch);
-        uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-        if (ch == 0) { dqo_bits = w.x; sum_bits = w.y; }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int i = ch * 4 + t - 2;
-            if (i >= 0 && i < r.nw) {
-                uint32_t s = ws[t];
-                d0 += __popc(r.planes[i] & s);
-                d1 += __popc(r.planes[r.nw + i] & s);
-                d2 += __popc(r.planes[2 * r.nw + i] & s);
-                d3 += __popc(r.planes[3 * r.nw + i] & s);
-            }
-        }
-    }
-    float dot = (float)(d0 + d1 * 2 + d2 * 4 + d3 * 8);
+// rabitq.rs:166-218: the float tail of QueryVector::similarity from the integer dot product -> (estimate, error bound)
+__device__ __forceinline__ void rq_finish(const RqCtx& r, uint32_t idot, uint32_t dqo_bits, uint32_t sum_bits, float& estimate, float& error) {
+    float dot = (float)idot;
     float dqo = __uint_as_float(dqo_bits);
     float t1 = __fmul_rn(__fdiv_rn(__fmul_rn(2.0f, r.delta), r.root_dim), dot);
     float t2 = __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, r.low), (float)sum_bits), r.root_dim);
@@ -74,65 +55,66 @@ __device__ __forceinline__ void rq_estimate(const RqCtx& r, const unsigned char*
     error = __fdiv_rn(__fmul_rn(__fsqrt_rn(__fdiv_rn(__fsub_rn(1.0f, dd), dd)), RABITQ_EPSILON), r.root_dim);
 }
 
-// Expand `node` ranking by the estimate.  Warp 0: lane = neighbour (visited test + code fetch + estimate + admission); the last
-// warp prefetches the adjacency row of the predicted next candidate (as hs_expand).  Leaves todo_key[0 .. stride) (0 = not
-// admitted), s_ntodo, s_nadmit, s_best_next for hs_merge<false>.
+// weighted popcount of one 16-byte chunk of a code against the four query bit planes (words -2, -1 of chunk 0 are the header)
+__device__ __forceinline__ uint32_t rq_chunk_dot(const RqCtx& r, int ch, uint4 w) {
+    uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int i = ch * 4 + t - 2;
+        if (i >= 0 && i < r.nw) {
+            uint32_t s = ws[t];
+            d0 += __popc(r.planes[i] & s);
+            d1 += __popc(r.planes[r.nw + i] & s);
+            d2 += __popc(r.planes[2 * r.nw + i] & s);
+            d3 += __popc(r.planes[3 * r.nw + i] & s);
+        }
+    }
+    return d0 + d1 * 2 + d2 * 4 + d3 * 8;   // exact integer arithmetic: any summation order gives the reference's value
+}
+
+// One thread, one code (16-byte aligned, `stride` bytes, zero padded).  The chunk loads are issued eight at a time BEFORE any of
+// them is consumed: a code costs one HBM latency, not one per 16 bytes.
+__device__ __forceinline__ void rq_estimate(const RqCtx& r, const unsigned char* __restrict__ code, int stride, float& estimate, float& error) {
+    const uint4* c4 = reinterpret_cast<const uint4*>(code);
+    uint32_t idot = 0, dqo_bits = 0, sum_bits = 0;
+    const int nchunks = stride >> 4;
+    for (int c0 = 0; c0 < nchunks; c0 += 8) {
+        uint4 w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = c0 + j < nchunks ? __ldg(c4 + c0 + j) : make_uint4(0, 0, 0, 0);
+        if (c0 == 0) { dqo_bits = w[0].x; sum_bits = w[0].y; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (c0 + j < nchunks) idot += rq_chunk_dot(r, c0 + j, w[j]);
+    }
+    rq_finish(r, idot, dqo_bits, sum_bits, estimate, error);
+}
+
+// Expand `node` ranking by the estimate.  The whole CTA works on one adjacency row: EIGHT LANES PER NEIGHBOUR (32 neighbours per
+// pass of 256 threads).  Lane j of a group loads 16-byte chunk j (j + 8, ...) of the neighbour's code -- the 112 bytes of a
+// 768-d code arrive as seven adjacent 16-byte requests of one warp instruction -- and takes its weighted popcount; three
+// shuffles add the eight partial sums (integers: exact in any order).  The group's first lane tests the visited set (global
+// table: the atomicCAS and the code loads are in flight together, codes of visited neighbours are fetched for nothing) and
+// finishes the estimate.  Admitted keys are compacted into todo_key[0 .. nadmit) (their order does not matter: hs_merge ranks
+// by key).  The last warp first prefetches the adjacency row of the predicted next candidate (as hs_expand) and publishes its
+// list position (*s_pred) for the caller's nothing-admitted fast path.
+// Counters live in s_cnt[parity of the hop][admitted, fresh, overflow]: thread 0 folds them after the barrier and clears the
+// other parity for the next hop, so no extra barrier is needed to reset them.
 template <bool GLOBAL_VIS>
-__device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, uint32_t node, int layer, int ef, int best) {
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int stride = G.stride(layer);
-    unsigned cur = c.hop & 1u;
-    if (warp == 0) {
-        const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
-        bool hit = c.pref_node[cur] == node;
-        const uint32_t* row = G.row(node, layer);
-        int len = *c.s_len;
-        uint64_t wkey = len >= ef ? c.A[len - 1] : 0;
-        int nadmit = 0, nfresh = 0;
-        bool ov = false;
-        for (int e0 = 0; e0 < stride; e0 += 32) {
-            uint32_t y = NIL;
-            if (e0 + lane < stride) y = hit ? prow[e0 + lane] : __ldg(row + e0 + lane);
-            bool valid = y != NIL, fresh = false;
-            float est = 0.0f, err = 0.0f;
-            if (valid) {
-                if (GLOBAL_VIS) {
-                    // the code loads inside rq_estimate do not depend on the CAS: both are in flight together
-                    uint32_t h = (y * 2654435761u) >> (32 - r.gv_bits);
-                    uint32_t old;
-                    bool full = *c.s_hash_count >= r.gv_limit;
-                    if (full) { ov = true; old = y; }
-                    else {
-                        while (true) {
-                            old = atomicCAS(&r.gvis[h], NIL, y);
-                            if (old == NIL || old == y) break;
-                            h = (h + 1) & r.gv_mask;
-                        }
-                    }
-                    rq_estimate(r, a.codes + (size_t)y * a.code_stride, a.code_stride, est, err);
-                    fresh = old == NIL;
-                } else {
-                    fresh = hash_insert(c, y, ov);
-                    if (fresh) rq_estimate(r, a.codes + (size_t)y * a.code_stride, a.code_stride, est, err);
-                }
-            }
-            uint64_t key = fresh ? make_key(est, y, 1) : 0;
-            bool admit = key > wkey;   // layer_search (search.rs:286): better than the worst of a full list (key 0 never is)
-            if (e0 + lane < stride) c.todo_key[e0 + lane] = admit ? key : 0;
-            nfresh += __popc(__ballot_sync(0xFFFFFFFFu, fresh));
-            nadmit += __popc(__ballot_sync(0xFFFFFFFFu, admit));
-        }
-        if (__any_sync(0xFFFFFFFFu, ov) && lane == 0) c.n_overflow++;
-        if (lane == 0) {
-            *c.s_ntodo = stride;
-            *c.s_hash_count += nfresh;
-            *c.s_best_next = INT_MAX;
-            *c.s_nadmit = nadmit;
-            c.n_expand++;
-            r.n_quant += nfresh;
-        }
-    } else if (warp == HS_WARPS - 1) {
-        int len = *c.s_len;
+__device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, uint32_t node, int layer, int ef, int best,
+                                 int (*s_cnt)[4], int* s_pred) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 7;
+    const int stride = G.stride(layer);
+    const unsigned cur = c.hop & 1u;
+    int* cnt = s_cnt[cur];
+    c.s_ntodo = cnt;        // hs_merge reads the number of todo keys and of admitted keys: both = cnt[0]
+    c.s_nadmit = cnt;
+    const int len = *c.s_len;
+    const uint64_t wkey = len >= ef ? c.A[len - 1] : 0;
+    const int visited = *c.s_hash_count;       // stable during the expansion (thread 0 updates it after the barrier)
+    if (threadIdx.x == 0) *c.s_best_next = INT_MAX;   // hs_merge's atomicMin target: reset before the barrier below
+    if (warp == HS_WARPS - 1) {
         int pred = -1;
         for (int i0 = best + 1; i0 < len && pred < 0; i0 += 32) {
             int i = i0 + lane;
@@ -146,11 +128,78 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
             uint32_t* dst = c.pref_row + (cur ^ 1u) * HS_MAX_ROW;
             for (int e = lane; e < stride; e += 32) cp_async4(dst + e, row2 + e);
         }
-        if (lane == 0) c.pref_node[cur ^ 1u] = pnode;
-        cp_async_commit_wait_all();
+        if (lane == 0) { c.pref_node[cur ^ 1u] = pnode; *s_pred = pred; }
     }
+    const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
+    const bool hit = c.pref_node[cur] == node;
+    const uint32_t* row = G.row(node, layer);
+    const int nchunks = a.code_stride >> 4;
+    for (int e0 = 0; e0 < stride; e0 += HS_THREADS / 8) {
+        const int e = e0 + (int)(threadIdx.x >> 3);
+        uint32_t y = NIL;
+        if (e < stride) y = hit ? prow[e] : __ldg(row + e);
+        const bool valid = y != NIL;
+        bool fresh = false, ov = false;
+        const uint4* c4 = reinterpret_cast<const uint4*>(a.codes + (size_t)(valid ? y : 0) * a.code_stride);
+        uint32_t idot = 0, dqo_bits = 0, sum_bits = 0;
+        if (GLOBAL_VIS) {
+            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;       // up to 256 bytes of code per pass (d <= 1984); longer codes loop below
+            if (valid && sub < nchunks) w0 = __ldg(c4 + sub);
+            if (valid && sub + 8 < nchunks) w1 = __ldg(c4 + sub + 8);
+            if (valid && sub == 0) {
+                if (visited >= r.gv_limit) ov = true;
+                else {
+                    uint32_t h = (y * 2654435761u) >> (32 - r.gv_bits);
+                    while (true) {
+                        uint32_t old = atomicCAS(&r.gvis[h], NIL, y);
+                        if (old == NIL) { fresh = true; break; }
+                        if (old == y) break;
+                        h = (h + 1) & r.gv_mask;
+                    }
+                }
+            }
+            if (valid) {
+                if (sub < nchunks) idot += rq_chunk_dot(r, sub, w0);
+                if (sub + 8 < nchunks) idot += rq_chunk_dot(r, sub + 8, w1);
+                for (int ch = sub + 16; ch < nchunks; ch += 8) idot += rq_chunk_dot(r, ch, __ldg(c4 + ch));
+            }
+            dqo_bits = w0.x; sum_bits = w0.y;
+        } else {
+            if (valid && sub == 0) fresh = hash_insert(c, y, ov);
+            fresh = __shfl_sync(0xFFFFFFFFu, fresh, lane & ~7);
+            if (fresh) {
+                uint4 w0 = make_uint4(0, 0, 0, 0);
+                if (sub < nchunks) { w0 = __ldg(c4 + sub); idot += rq_chunk_dot(r, sub, w0); }
+                for (int ch = sub + 8; ch < nchunks; ch += 8) idot += rq_chunk_dot(r, ch, __ldg(c4 + ch));
+                dqo_bits = w0.x; sum_bits = w0.y;
+            }
+        }
+        idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 1);
+        idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 2);
+        idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 4);
+        bool admit = false;
+        if (sub == 0 && fresh) {
+            float est, err;
+            rq_finish(r, idot, dqo_bits, sum_bits, est, err);
+            uint64_t key = make_key(est, y, 1);
+            admit = key > wkey;          // layer_search (search.rs:286): better than the worst of a full list
+            if (admit) c.todo_key[atomicAdd(&cnt[0], 1)] = key;
+        }
+        unsigned mf = __ballot_sync(0xFFFFFFFFu, sub == 0 && fresh);
+        if (lane == 0 && mf) atomicAdd(&cnt[1], __popc(mf));
+        if (ov) cnt[2] = 1;
+    }
+    if (warp == HS_WARPS - 1) cp_async_commit_wait_all();
     c.hop++;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        *c.s_hash_count = visited + cnt[1];
+        c.n_expand++;
+        r.n_quant += cnt[1];
+        if (cnt[2]) c.n_overflow++;
+        int* nxt = s_cnt[cur ^ 1u];
+        nxt[0] = 0; nxt[1] = 0; nxt[2] = 0;
+    }
 }
 
 // Start a layer search on the list in c.A: every entry unexpanded, visited set = the list's ids.
@@ -179,12 +228,23 @@ __device__ inline void rq_reseed(SearchCtx& c, RqCtx& r) {
 }
 
 template <bool GLOBAL_VIS>
-__device__ inline void rq_layer_search(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, int layer, int ef) {
+__device__ inline void rq_layer_search(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, int layer, int ef, int (*s_cnt)[4], int* s_pred) {
     while (true) {
         int best = *c.s_best, len = *c.s_len;
         if (best >= len) break;
         uint64_t ckey = c.A[best];
-        rq_expand<GLOBAL_VIS>(G, c, a, r, key_id(ckey), layer, ef, best);
+        rq_expand<GLOBAL_VIS>(G, c, a, r, key_id(ckey), layer, ef, best, s_cnt, s_pred);
+        if (*c.s_nadmit == 0) {
+            // nothing admitted (the common case once the list is full): the list only loses the expanded flag of `best`, and the
+            // next candidate is the first unexpanded entry after it -- the one the prefetching warp has just located.
+            if (threadIdx.x == 0) {    // (every thread read *s_best before rq_expand's barrier and *s_nadmit's slot is not touched until the next one)
+                c.A[best] &= ~1ull;
+                int pred = *s_pred;
+                *c.s_best = pred >= 0 ? pred : len;
+            }
+            __syncthreads();
+            continue;
+        }
         hs_merge<false>(c, ef, best);
     }
 }
@@ -195,6 +255,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, Gr
     __shared__ int s_ints[8];
     __shared__ unsigned int s_work;
     __shared__ int s_wtot[RQ_RC / 32], s_total, s_hlen;
+    __shared__ int s_cnt[2][4], s_pred;
     __shared__ float s_best_k;
     SearchCtx c;
     RqCtx r;
@@ -237,6 +298,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, Gr
         const float* qsrc = a.queries + (size_t)q * V.ld;
         for (int i = threadIdx.x; i < ng; i += blockDim.x) reinterpret_cast<float4*>(c.qvec)[i] = reinterpret_cast<const float4*>(qsrc)[i];
         for (int i = threadIdx.x; i < 4 * r.nw; i += blockDim.x) planes[i] = a.planes[(size_t)q * 4 * r.nw + i];
+        if (threadIdx.x < 8) s_cnt[threadIdx.x >> 2][threadIdx.x & 3] = 0;   // closest_up's hops (hs_expand) change the parity between queries
         RabitqQueryParams qp = qparams[q];
         r.low = qp.low; r.delta = qp.delta; r.sum_quantized = qp.sum_quantized;
         __syncthreads();
@@ -253,13 +315,14 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, Gr
         __syncthreads();
         for (int layer = (int)G.entry_layer; layer > 0; --layer) {   // search.rs:321-327: one best node per upper layer
             rq_reseed<false>(c, r);
-            rq_layer_search<false>(G, c, a, r, layer, 1);
+            rq_layer_search<false>(G, c, a, r, layer, 1, s_cnt, &s_pred);
             __syncthreads();
         }
         rq_reseed<true>(c, r);
-        rq_layer_search<true>(G, c, a, r, 0, a.last_k);             // search.rs:335-345
+        rq_layer_search<true>(G, c, a, r, 0, a.last_k, s_cnt, &s_pred);             // search.rs:335-345
         __syncthreads();
 
+        c.s_ntodo = &s_ints[3]; c.s_nadmit = &s_ints[6];   // rq_expand pointed both at its counter slot; closest_up_nodes (hs_expand) needs two
         // ---- rerank_top (rabitq.rs:222-244) over the list, best estimate first ----
         const int len = *c.s_len;
         if (threadIdx.x == 0) { s_hlen = 0; s_best_k = 0.0f; }

@@ -118,7 +118,7 @@ __device__ inline void hs_reseed(SearchCtx& c) {
 // Speculation: while warp 0 works, the last warp starts an asynchronous copy (cp.async) of the adjacency
 // row of the node that will be expanded next if no new neighbour outranks it -- `pred_idx` in the list --
 // into the other half of a double buffer; the row's HBM latency then overlaps this expansion's vector loads.
-template <bool CU, int NG>
+template <bool CU, int NG, int W = HS_WARPS, bool PAIR = false>
 __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& c, uint32_t node, int layer, int ef, float min_score, int best) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int stride = G.stride(layer);
@@ -145,7 +145,7 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
             *c.s_nadmit = 0;
             c.n_expand++;
         }
-    } else if (warp == HS_WARPS - 1) {
+    } else if (warp == W - 1) {
         int len = *c.s_len;
         int pred = -1;
         if (CU) {
@@ -170,20 +170,35 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
     int ntodo = *c.s_ntodo, len = *c.s_len;
     uint64_t wkey = (!CU && len >= ef) ? c.A[len - 1] : 0;
     int ng = V.ld >> 2;
-    for (int j = warp; j < ntodo; j += HS_WARPS) {
-        uint32_t y = c.todo_id[j];
-        float vnorm = V.sim != SIM_DOT ? __ldg(V.norms + y) : 0.0f;
-        float ab = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)y * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
-        if (lane == 0) {
-            float s = sim_from_parts(V.sim, ab, vnorm, c.qnorm);
-            uint64_t key = make_key(s, y, 1);
-            bool admit = CU ? (s >= min_score) : (key > wkey);
-            c.todo_key[j] = admit ? key : 0;
-            if (admit) atomicAdd(c.s_nadmit, 1);
-            c.n_dist++;
+    auto finish = [&](int j, uint32_t y, float ab, float vnorm) {
+        float s = sim_from_parts(V.sim, ab, vnorm, c.qnorm);
+        uint64_t key = make_key(s, y, 1);
+        bool admit = CU ? (s >= min_score) : (key > wkey);
+        c.todo_key[j] = admit ? key : 0;
+        if (admit) atomicAdd(c.s_nadmit, 1);
+        c.n_dist++;
+    };
+    if constexpr (PAIR) {   // two rows in flight per warp (fewer warps per query, more queries per SM)
+        for (int j = warp; j < ntodo; j += 2 * W) {
+            uint32_t y0 = c.todo_id[j];
+            bool two = j + W < ntodo;
+            uint32_t y1 = two ? c.todo_id[j + W] : y0;
+            float n0 = V.sim != SIM_DOT ? __ldg(V.norms + y0) : 0.0f, n1 = (two && V.sim != SIM_DOT) ? __ldg(V.norms + y1) : 0.0f;
+            float ab0, ab1;
+            if (two) warp_dot2_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)y0 * V.ld), reinterpret_cast<const float4*>(V.vecs + (size_t)y1 * V.ld),
+                                     reinterpret_cast<const float4*>(c.qvec), ng, lane, ab0, ab1);
+            else { ab0 = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)y0 * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane); ab1 = 0.0f; }
+            if (lane == 0) { finish(j, y0, ab0, n0); if (two) finish(j + W, y1, ab1, n1); }
+        }
+    } else {
+        for (int j = warp; j < ntodo; j += W) {
+            uint32_t y = c.todo_id[j];
+            float vnorm = V.sim != SIM_DOT ? __ldg(V.norms + y) : 0.0f;
+            float ab = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)y * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
+            if (lane == 0) finish(j, y, ab, vnorm);
         }
     }
-    if (warp == HS_WARPS - 1) cp_async_commit_wait_all();
+    if (warp == W - 1) cp_async_commit_wait_all();
     c.hop++;
     __syncthreads();
 }
@@ -234,13 +249,13 @@ __device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
 }
 
 // hnsw/search.rs:242-304 on the list held in shared memory.
-template <int NG>
+template <int NG, int W = HS_WARPS, bool PAIR = false>
 __device__ inline void hs_layer_search(const VecDev& V, const GraphDev& G, SearchCtx& c, int layer, int ef) {
     while (true) {
         int best = *c.s_best, len = *c.s_len;
         if (best >= len) break;
         uint64_t ckey = c.A[best];
-        hs_expand<false, NG>(V, G, c, key_id(ckey), layer, ef, 0.0f, best);
+        hs_expand<false, NG, W, PAIR>(V, G, c, key_id(ckey), layer, ef, 0.0f, best);
         hs_merge<false>(c, ef, best);
     }
 }
@@ -274,7 +289,7 @@ __device__ inline bool hs_passes(const VecDev& V, const SearchArgs& a, uint32_t 
 }
 
 // hnsw/search.rs:188-240.  Results go straight to out_ids/out_scores (already descending).
-template <int NG>
+template <int NG, int W = HS_WARPS, bool PAIR = false>
 __device__ inline int hs_closest_up(const VecDev& V, const GraphDev& G, SearchCtx& c, const SearchArgs& a, uint32_t* out_ids, float* out_scores) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     hs_reseed(c);
@@ -297,7 +312,7 @@ __device__ inline int hs_closest_up(const VecDev& V, const GraphDev& G, SearchCt
         __syncthreads();
         nacc += *c.s_flag;
         if (nacc == a.k) break;  // 214
-        hs_expand<true, NG>(V, G, c, node, 0, 0, a.min_score, 0);
+        hs_expand<true, NG, W, PAIR>(V, G, c, node, 0, 0, a.min_score, 0);
         hs_merge<true>(c, a.cu_cap, 0);
     }
     return nacc;
@@ -305,11 +320,11 @@ __device__ inline int hs_closest_up(const VecDev& V, const GraphDev& G, SearchCt
 
 // The tail of HnswSearcher::search for query q: closest_up_nodes on the list in c.A (search.rs:369-375), the final stable sort
 // (search.rs:381) and the NIL padding of the outputs.
-template <int NG>
+template <int NG, int W = HS_WARPS, bool PAIR = false>
 __device__ inline void hs_emit_results(const VecDev& V, const GraphDev& G, SearchCtx& c, const SearchArgs& a, unsigned int q) {
     uint32_t* oi = a.out_ids + (size_t)q * a.k;
     float* os = a.out_scores + (size_t)q * a.k;
-    int nacc = hs_closest_up<NG>(V, G, c, a, oi, os);
+    int nacc = hs_closest_up<NG, W, PAIR>(V, G, c, a, oi, os);
     __syncthreads();
     // search.rs:381 `filtered_result.sort_by(|a, b| b.1.total_cmp(&a.1))`: stable, descending.
     // (closest_up_nodes can accept a late-found neighbour that outranks earlier results.)
@@ -334,8 +349,11 @@ __device__ inline void hs_emit_results(const VecDev& V, const GraphDev& G, Searc
     if (threadIdx.x == 0) a.out_counts[q] = nacc;
 }
 
-template <int NG>
-__global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, GraphDev G, SearchArgs a) {
+// W warps per CTA.  W = 8: one row per warp in flight, 4 CTAs per SM (592 queries resident).  W = 4 (PAIR): two rows per warp in
+// flight, 7 CTAs per SM -- 1036 queries resident, so a batch of 1024 runs as ONE wave instead of 592 + 432 (the second wave of
+// the 8-warp shape leaves 27 % of the CTA slots empty while it runs).
+template <int NG, int W = HS_WARPS, bool PAIR = false>
+__global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_search_kernel(VecDev V, GraphDev G, SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ints[8];
     __shared__ unsigned int s_work;
@@ -391,7 +409,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
             if (a.mode == 0) ef = layer == 0 ? a.ef0 : 1;
             else ef = layer <= top ? a.efC : 1;
             hs_reseed(c);
-            hs_layer_search<NG>(V, G, c, layer, ef);
+            hs_layer_search<NG, W, PAIR>(V, G, c, layer, ef);
             __syncthreads();
             if (a.mode == 1 && layer <= top && layer < HS_MAX_LAYERS) {
                 int len = *c.s_len;
@@ -410,7 +428,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_search_kernel(VecDev V, Gr
         if (a.mode == 1 && threadIdx.x == 0)
             for (int layer = (int)G.entry_layer + 1; layer <= top && layer < HS_MAX_LAYERS; ++layer) a.found_count[(size_t)q * HS_MAX_LAYERS + layer] = 0;
 
-        if (a.mode == 0) hs_emit_results<NG>(V, G, c, a, q);
+        if (a.mode == 0) hs_emit_results<NG, W, PAIR>(V, G, c, a, q);
     }
     // counters: n_dist lives in lane 0 of every warp, the rest in thread 0
     if (lane == 0 && c.n_dist) atomicAdd(&a.counters[0], c.n_dist);

@@ -23,8 +23,8 @@
 //            four per stage; tcgen05.commit releases the stage; accumulators double-buffered in TMEM (2 x 256 columns);
 //   warp 2   TMEM allocation;
 //   warps 4-7 epilogue: thread = query row = TMEM lane; tcgen05.ld 32 columns at a time, cosine scaling, eligibility bit,
-//            running top-L of the row in REGISTERS (unsorted + its minimum; the update is branch-free and entered only when a
-//            lane of the warp has a score above its row's minimum).
+//            running top-L of the row in REGISTERS (unsorted + its minimum), fed through a per-row staging area in shared memory
+//            so that the (warp-wide) list update runs once per ~8-16 candidates of the busiest row, not once per column.
 // scan_tc_refine_kernel: one CTA per query: overflow test, tau, survivors, exact re-scoring (one warp per survivor),
 //   min_score, top-k -- or the exact scan of the whole segment for an overflowed query.
 #pragma once
@@ -46,8 +46,9 @@ constexpr int TC2_L = 24;             // candidates kept per (query, chunk)
 constexpr int TC2_KMAX = 16;          // the filter path serves k <= TC2_KMAX
 constexpr int TC2_THREADS = 256;
 constexpr uint32_t TC2_A_BYTES = TC2_M * 128, TC2_B_BYTES = TC2_N * 128, TC2_STAGE_BYTES = TC2_A_BYTES + TC2_B_BYTES;
+constexpr int TC2_STAGE_ROWS = 16;    // staged candidates per query row between two merges into the register list
 constexpr size_t TC2_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)TC2_STAGES * TC2_STAGE_BYTES + 2 * TC2_N * 4 /* 1/|v| */ +
-                                  2 * (TC2_N / 32) * 4 /* eligibility */ + 256;
+                                  2 * (TC2_N / 32) * 4 /* eligibility */ + (size_t)TC2_STAGE_ROWS * TC2_M * 8 /* staging */ + 256;
 constexpr float TC2_EPS = 2.2e-3f;
 constexpr int TC2_SURV_CAP = 512;     // survivors per query the refine kernel re-scores; more => exact scan
 
@@ -99,6 +100,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
     unsigned char* stages = smem;
     float* inv_vn = reinterpret_cast<float*>(smem + (size_t)TC2_STAGES * TC2_STAGE_BYTES);     // [2][256]
     uint32_t* elig = reinterpret_cast<uint32_t*>(inv_vn + 2 * TC2_N);                          // [2][8]
+    float* stg_sc = reinterpret_cast<float*>(elig + 2 * (TC2_N / 32));                         // [TC2_STAGE_ROWS][128] staged scores ...
+    uint32_t* stg_id = reinterpret_cast<uint32_t*>(stg_sc + TC2_STAGE_ROWS * TC2_M);           // ... and ids of the epilogue rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = V.ld / TC2_KB;
     const Tc2Sched sch(a);
@@ -179,8 +182,33 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
             uint32_t li[TC2_L];
 #pragma unroll
             for (int i = 0; i < TC2_L; ++i) { ls[i] = -INFINITY; li[i] = NIL; }
-            int cnt = 0, minpos = 0;
+            int cnt = 0, minpos = 0, n_st = 0;
             float thr = -INFINITY;       // scores <= thr cannot enter the list (-inf until it is full)
+            // Candidates that beat the row's threshold are first appended to a per-row staging area in shared memory ([slot][row]: the
+            // lanes of a warp hit 32 different banks) and merged into the register list only when some row's area is nearly full: the
+            // list update -- ~70 predicated instructions, executed by the whole warp whenever ANY lane needs it -- then runs a few
+            // dozen times per row share instead of once per column.  Staged entries keep their column order and are re-tested against
+            // the up-to-date threshold at merge time, so the list ends up exactly as if every column had been merged at once.
+            auto merge_staged = [&]() {
+                for (int t = 0; t < n_st; ++t) {
+                    const float sc = stg_sc[t * TC2_M + row];
+                    if (sc > thr) {
+                        const uint32_t id = stg_id[t * TC2_M + row];
+                        const int pos = cnt < TC2_L ? cnt : minpos;
+#pragma unroll
+                        for (int i = 0; i < TC2_L; ++i) if (i == pos) { ls[i] = sc; li[i] = id; }   // static indices: predicated moves
+                        if (cnt < TC2_L) ++cnt;
+                        if (cnt == TC2_L) {
+                            float m = ls[0];
+                            int mp = 0;
+#pragma unroll
+                            for (int i = 1; i < TC2_L; ++i) if (ls[i] < m) { m = ls[i]; mp = i; }
+                            thr = m; minpos = mp;
+                        }
+                    }
+                }
+                n_st = 0;
+            };
             for (int ch = sch.slot; ch < a.n_chunks; ch += sch.slots)
                 for (int t = 0; t < TC2_TILES; ++t) {
                     int v0 = ch * TC2_CHUNK + t * TC2_N;
@@ -220,22 +248,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
                             float sc = __uint_as_float(r[j]);
                             if (V.sim == SIM_COSINE) sc = sc * inv_qn * inv_vn[acc * TC2_N + c0 + j];
                             const bool pass = ((ew >> j) & 1u) && sc > thr;
-                            if (__any_sync(0xFFFFFFFFu, pass)) {          // warp-uniform: most columns beat no row's minimum
-                                if (pass) {
-                                    const int pos = cnt < TC2_L ? cnt : minpos;
-                                    const uint32_t id = (uint32_t)v0 + c0 + j;
-#pragma unroll
-                                    for (int i = 0; i < TC2_L; ++i) if (i == pos) { ls[i] = sc; li[i] = id; }   // static indices: predicated moves
-                                    if (cnt < TC2_L) ++cnt;
-                                    if (cnt == TC2_L) {
-                                        float m = ls[0];
-                                        int mp = 0;
-#pragma unroll
-                                        for (int i = 1; i < TC2_L; ++i) if (ls[i] < m) { m = ls[i]; mp = i; }
-                                        thr = m; minpos = mp;
-                                    }
-                                }
+                            if (pass) {                                   // predicated stores: the row's staging area, in column order
+                                stg_sc[n_st * TC2_M + row] = sc;
+                                stg_id[n_st * TC2_M + row] = (uint32_t)v0 + c0 + j;
+                                ++n_st;
                             }
+                            if ((j & 7) == 7 && __any_sync(0xFFFFFFFFu, n_st > TC2_STAGE_ROWS - 8)) merge_staged();
                         }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -243,6 +261,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                     ++tcount;
                 }
+            merge_staged();
             if (q < a.nq) {
                 float* os = a.cand_score + ((size_t)q * a.slots + sch.slot) * TC2_L;
                 uint32_t* oi = a.cand_id + ((size_t)q * a.slots + sch.slot) * TC2_L;

@@ -258,6 +258,11 @@ class TextSegment:
                                 ptr(total), None))
         return docs, scores, counts, total
 
+    def set_doc_keys(self, keys: Optional[np.ndarray]):
+        """Caller keys of the documents (paragraph ids) for rank fusion; None = the document number."""
+        k = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+        check(_lib.load().nidx_txt_set_doc_keys(self._h, ptr(k)))
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         check(_lib.load().nidx_txt_last_kernel_ms(self._h, C.byref(ms)))
