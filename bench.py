@@ -527,6 +527,36 @@ def main():
         inline_ms = float(t.item()) / args.steps
         dist.barrier()
 
+    # ---- the same steps with TWO batches in flight (N = 1) ----------------------------------------------
+    # A batch of 1024 queries runs as 592 + 432 CTAs (4 resident per SM): while the second wave drains, 27 % of the CTA slots are
+    # empty.  The reference's searcher serves concurrent requests against one shared index (shard_search.rs:139-155); with the next
+    # batch issued on a second stream its CTAs fill those slots.  Same K steps, inputs in HBM, events across both streams.
+    two_streams = None
+    if not multi and not pipelined:
+        st2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        outs2 = [out, (torch.empty_like(out[0]), torch.empty_like(out[1]), torch.empty_like(out[2]))]
+        for i in range(args.warmup):
+            with torch.cuda.stream(st2[i % 2]):
+                seg.search(queries[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=outs2[i % 2])
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e_end = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        launches_a = L.nidx_launch_count()
+        with clocks:
+            e0.record(st2[0])
+            st2[1].wait_event(e0)
+            for i in range(args.warmup, n_batches):
+                j = (i - args.warmup) % 2
+                with torch.cuda.stream(st2[j]):
+                    seg.search(queries[i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=outs2[j])
+            for j in range(2):
+                e_end[j].record(st2[j])
+            torch.cuda.synchronize()
+        ms2 = max(e0.elapsed_time(e_end[0]), e0.elapsed_time(e_end[1]))
+        two_streams = {"value": nq * args.steps / (ms2 * 1e-3), "unit": "queries/s", "ms_per_step": ms2 / args.steps, "steps": args.steps,
+                       "gpu_launches": int(L.nidx_launch_count() - launches_a),
+                       "note": "the same K steps issued on two streams alternately: batch i + 1 starts while the second wave of batch i drains"}
+
     # ---- recall + roofline accounting (separate, synchronous passes) ----------------------------------
     ids, _, _ = seg.search(queries[args.warmup], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)
     torch.cuda.synchronize()
@@ -701,6 +731,7 @@ def main():
                        "data_gen": ({"latent": f"latent={args.latent} noise={args.noise} normalised", "gauss": "N(0,1) normalised (BASELINE.md 3)",
                                      "clustered": "4096 centres, normalise(centre + 0.1 * unit fuzz) (BASELINE.md 3)"}[args.data]
                                     + "; queries = data point + 0.05 * unit noise")},
+            "two_batches_in_flight": two_streams,
             "merged_qps": nq * args.steps / (ms_total * 1e-3),
             "exchange_in_line_ms_per_step": inline_ms,
             "recall_at_10": recall,

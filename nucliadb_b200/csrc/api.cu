@@ -88,19 +88,30 @@ struct Workspace {
 struct WorkspacePool {
     std::mutex mu;
     std::vector<Workspace*> all;
+    // A free workspace last used on this stream (stream order protects it), else one whose last call has completed, else a new one
+    // (up to MAX_POOL: calls issued from one host thread on alternating streams then overlap on the device instead of the second
+    // waiting for the first one's buffers), else the host waits for a free one's last call.
+    static constexpr size_t MAX_POOL = 8;
     Workspace* acquire(cudaStream_t stream) {
         std::lock_guard<std::mutex> g(mu);
+        Workspace* pick = nullptr;
         for (Workspace* w : all)
-            if (!w->busy) {
-                w->busy = true;
-                if (w->last_stream != stream && w->done) cudaEventSynchronize(w->done);
-                return w;
-            }
-        Workspace* w = new Workspace();
-        cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming);
-        w->busy = true;
-        all.push_back(w);
-        return w;
+            if (!w->busy && w->last_stream == stream) { pick = w; break; }
+        if (!pick) {
+            for (Workspace* w : all)
+                if (!w->busy && (!w->done || cudaEventQuery(w->done) == cudaSuccess)) { pick = w; break; }
+            (void)cudaGetLastError();   // cudaErrorNotReady from a query is not an error: do not leave it for the next cudaGetLastError()
+        }
+        if (!pick && all.size() >= MAX_POOL)
+            for (Workspace* w : all)
+                if (!w->busy) { cudaEventSynchronize(w->done); pick = w; break; }
+        if (!pick) {
+            pick = new Workspace();
+            cudaEventCreateWithFlags(&pick->done, cudaEventDisableTiming);
+            all.push_back(pick);
+        }
+        pick->busy = true;
+        return pick;
     }
     void release(Workspace* w, cudaStream_t stream) {
         cudaEventRecord(w->done, stream);
@@ -692,6 +703,18 @@ static hs_kernel_t pick_search_kernel_w4(int ld) {
     return nullptr;
 }
 
+static hs_kernel_t pick_rabitq_walk_kernel_w4(int ld) {
+    if (ld % 128 == 0) switch (ld / 128) {
+        case 2: return hnsw_rabitq_kernel<2, 4>;
+        case 3: return hnsw_rabitq_kernel<3, 4>;
+        case 4: return hnsw_rabitq_kernel<4, 4>;
+        case 6: return hnsw_rabitq_kernel<6, 4>;
+        case 8: return hnsw_rabitq_kernel<8, 4>;
+        default: break;
+    }
+    return hnsw_rabitq_kernel<0, 4>;
+}
+
 static hs_kernel_t pick_search_kernel_w8pair(int ld) {
     if (ld % 128 == 0) switch (ld / 128) {
         case 3: return hnsw_search_kernel<3, 8, true>;
@@ -1142,10 +1165,24 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         if (const char* e = getenv("NIDX_B200_RQ_VISITED_BITS")) { int b = atoi(e); if (b >= 12 && b <= 22) gv_bits = b; }
         size_t smem = rq_smem_bytes(s->ld, s->d, list_cap, hash_bits, k);
         if (smem > 200 * 1024) return fail(NIDX_EINVAL, "quantised HNSW search needs %zu bytes of shared memory (k=%d, dim=%d): too large", smem, k, s->d);
+        // CTA shape: the walk is bound by the ~1 000 dependent hops of a query, so what counts is how many queries are resident.
+        // 8 warps per query: 4 CTAs per SM; 4 warps: 7 per SM.  The 4-warp shape is taken when the batch does not fit one wave of the
+        // 8-warp shape (NIDX_B200_RQ_W = 4 / 8 forces one).
         hs_kernel_t kern = pick_rabitq_walk_kernel(s->ld);
+        int threads = HS_THREADS;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HS_THREADS, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        {
+            const char* ew = getenv("NIDX_B200_RQ_W");
+            int force = ew ? atoi(ew) : 0;
+            if (force == 4 || (force != 8 && nq > std::max(1, occ) * s->sm_count)) {
+                kern = pick_rabitq_walk_kernel_w4(s->ld);
+                threads = 128;
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+            }
+        }
         int grid = std::min(nq, std::max(1, occ) * s->sm_count);
         ENSURE(w.scores, ((size_t)grid << gv_bits) * 4);
         SearchArgs a;
@@ -1162,7 +1199,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
         CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
         CU(cudaEventRecord(s->ev_k0, stream));
-        kern<<<grid, HS_THREADS, smem, stream>>>(V, s->gdev(), a);
+        kern<<<grid, threads, smem, stream>>>(V, s->gdev(), a);
         CU(cudaEventRecord(s->ev_k1, stream));
         LAUNCHED();
         CU(cudaGetLastError());
@@ -1207,6 +1244,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         int grid = std::min(nq, std::max(1, occ) * s->sm_count);
+        if (const char* eg = getenv("NIDX_B200_HS_GRID")) { int gg = atoi(eg); if (gg > 0) grid = std::min(grid, gg); }
         CU(cudaEventRecord(s->ev_k0, stream));
         kern<<<grid, threads, smem, stream>>>(V, s->gdev(), a);
         CU(cudaEventRecord(s->ev_k1, stream));

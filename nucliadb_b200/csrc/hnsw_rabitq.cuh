@@ -100,9 +100,12 @@ __device__ __forceinline__ void rq_estimate(const RqCtx& r, const unsigned char*
 // list position (*s_pred) for the caller's nothing-admitted fast path.
 // Counters live in s_cnt[parity of the hop][admitted, fresh, overflow]: thread 0 folds them after the barrier and clears the
 // other parity for the next hop, so no extra barrier is needed to reset them.
-template <bool GLOBAL_VIS>
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+template <bool GLOBAL_VIS, int W>
 __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, uint32_t node, int layer, int ef, int best,
                                  int (*s_cnt)[4], int* s_pred) {
+    constexpr int NPG = W * 4;     // neighbours per pass: eight lanes each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7;
     const int stride = G.stride(layer);
@@ -114,7 +117,8 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
     const uint64_t wkey = len >= ef ? c.A[len - 1] : 0;
     const int visited = *c.s_hash_count;       // stable during the expansion (thread 0 updates it after the barrier)
     if (threadIdx.x == 0) *c.s_best_next = INT_MAX;   // hs_merge's atomicMin target: reset before the barrier below
-    if (warp == HS_WARPS - 1) {
+    const int nchunks = a.code_stride >> 4;
+    if (warp == W - 1) {
         int pred = -1;
         for (int i0 = best + 1; i0 < len && pred < 0; i0 += 32) {
             int i = i0 + lane;
@@ -133,63 +137,90 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
     const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
     const bool hit = c.pref_node[cur] == node;
     const uint32_t* row = G.row(node, layer);
-    const int nchunks = a.code_stride >> 4;
-    for (int e0 = 0; e0 < stride; e0 += HS_THREADS / 8) {
-        const int e = e0 + (int)(threadIdx.x >> 3);
-        uint32_t y = NIL;
-        if (e < stride) y = hit ? prow[e] : __ldg(row + e);
-        const bool valid = y != NIL;
-        bool fresh = false, ov = false;
-        const uint4* c4 = reinterpret_cast<const uint4*>(a.codes + (size_t)(valid ? y : 0) * a.code_stride);
-        uint32_t idot = 0, dqo_bits = 0, sum_bits = 0;
-        if (GLOBAL_VIS) {
-            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;       // up to 256 bytes of code per pass (d <= 1984); longer codes loop below
-            if (valid && sub < nchunks) w0 = __ldg(c4 + sub);
-            if (valid && sub + 8 < nchunks) w1 = __ldg(c4 + sub + 8);
-            if (valid && sub == 0) {
-                if (visited >= r.gv_limit) ov = true;
-                else {
-                    uint32_t h = (y * 2654435761u) >> (32 - r.gv_bits);
-                    while (true) {
-                        uint32_t old = atomicCAS(&r.gvis[h], NIL, y);
-                        if (old == NIL) { fresh = true; break; }
-                        if (old == y) break;
-                        h = (h + 1) & r.gv_mask;
+    for (int e0 = 0; e0 < stride; e0 += 2 * NPG) {
+        // two passes at once: every global request of both (codes, visited-set CAS) is in flight before anything is consumed
+        uint32_t y[2];
+        uint4 w0[2], w1[2];
+        bool valid[2], fresh[2] = {false, false}, ov = false;
+        const uint4* c4[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int e = e0 + p * NPG + (int)(threadIdx.x >> 3);
+            y[p] = NIL;
+            if (e < stride) y[p] = hit ? prow[e] : __ldg(row + e);
+            valid[p] = y[p] != NIL;
+            c4[p] = reinterpret_cast<const uint4*>(a.codes + (size_t)(valid[p] ? y[p] : 0) * a.code_stride);
+            w0[p] = make_uint4(0, 0, 0, 0); w1[p] = w0[p];
+            if (GLOBAL_VIS) {       // up to 256 bytes of code per neighbour here (d <= 1984); longer codes loop below
+                if (valid[p] && sub < nchunks) w0[p] = __ldg(c4[p] + sub);
+                if (valid[p] && sub + 8 < nchunks) w1[p] = __ldg(c4[p] + sub + 8);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            if (GLOBAL_VIS) {
+                if (valid[p] && sub == 0) {
+                    if (visited >= r.gv_limit) ov = true;
+                    else {
+                        uint32_t h = (y[p] * 2654435761u) >> (32 - r.gv_bits);
+                        while (true) {
+                            uint32_t old = atomicCAS(&r.gvis[h], NIL, y[p]);
+                            if (old == NIL) { fresh[p] = true; break; }
+                            if (old == y[p]) break;
+                            h = (h + 1) & r.gv_mask;
+                        }
                     }
                 }
-            }
-            if (valid) {
-                if (sub < nchunks) idot += rq_chunk_dot(r, sub, w0);
-                if (sub + 8 < nchunks) idot += rq_chunk_dot(r, sub + 8, w1);
-                for (int ch = sub + 16; ch < nchunks; ch += 8) idot += rq_chunk_dot(r, ch, __ldg(c4 + ch));
-            }
-            dqo_bits = w0.x; sum_bits = w0.y;
-        } else {
-            if (valid && sub == 0) fresh = hash_insert(c, y, ov);
-            fresh = __shfl_sync(0xFFFFFFFFu, fresh, lane & ~7);
-            if (fresh) {
-                uint4 w0 = make_uint4(0, 0, 0, 0);
-                if (sub < nchunks) { w0 = __ldg(c4 + sub); idot += rq_chunk_dot(r, sub, w0); }
-                for (int ch = sub + 8; ch < nchunks; ch += 8) idot += rq_chunk_dot(r, ch, __ldg(c4 + ch));
-                dqo_bits = w0.x; sum_bits = w0.y;
+            } else {
+                if (valid[p] && sub == 0) fresh[p] = hash_insert(c, y[p], ov);
+                fresh[p] = __shfl_sync(0xFFFFFFFFu, fresh[p], lane & ~7);
+                if (fresh[p]) {
+                    if (sub < nchunks) w0[p] = __ldg(c4[p] + sub);
+                    if (sub + 8 < nchunks) w1[p] = __ldg(c4[p] + sub + 8);
+                }
             }
         }
-        idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 1);
-        idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 2);
-        idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 4);
-        bool admit = false;
-        if (sub == 0 && fresh) {
-            float est, err;
-            rq_finish(r, idot, dqo_bits, sum_bits, est, err);
-            uint64_t key = make_key(est, y, 1);
-            admit = key > wkey;          // layer_search (search.rs:286): better than the worst of a full list
-            if (admit) c.todo_key[atomicAdd(&cnt[0], 1)] = key;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            uint32_t idot = 0;
+            if (valid[p] && (GLOBAL_VIS || fresh[p])) {
+                if (sub < nchunks) idot += rq_chunk_dot(r, sub, w0[p]);
+                if (sub + 8 < nchunks) idot += rq_chunk_dot(r, sub + 8, w1[p]);
+                for (int ch = sub + 16; ch < nchunks; ch += 8) idot += rq_chunk_dot(r, ch, __ldg(c4[p] + ch));
+            }
+            idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 1);
+            idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 2);
+            idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 4);
+            if (sub == 0 && fresh[p]) {
+                float est, err;
+                rq_finish(r, idot, w0[p].x, w0[p].y, est, err);       // chunk 0 starts with the code's header (dot_quant_original, sum_bits)
+                uint64_t key = make_key(est, y[p], 1);
+                if (key > wkey) c.todo_key[atomicAdd(&cnt[0], 1)] = key;   // layer_search (search.rs:286): better than the worst of a full list
+            }
+            unsigned mf = __ballot_sync(0xFFFFFFFFu, sub == 0 && fresh[p]);
+            if (lane == 0 && mf) atomicAdd(&cnt[1], __popc(mf));
         }
-        unsigned mf = __ballot_sync(0xFFFFFFFFu, sub == 0 && fresh);
-        if (lane == 0 && mf) atomicAdd(&cnt[1], __popc(mf));
         if (ov) cnt[2] = 1;
     }
-    if (warp == HS_WARPS - 1) cp_async_commit_wait_all();
+    if (warp == W - 1) {
+        cp_async_commit_wait_all();
+        if (GLOBAL_VIS) {
+            // The predicted next node's adjacency row is in shared memory now: pull its neighbours' codes and visited-table slots
+            // into L2 while this hop's merge runs (3.6 KB + 32 lines per hop; wasted when the prediction fails).
+            __syncwarp();
+            const uint32_t* nrow = c.pref_row + (cur ^ 1u) * HS_MAX_ROW;
+            if (c.pref_node[cur ^ 1u] != NIL)
+                for (int e = lane; e < stride; e += 32) {
+                    uint32_t y2 = nrow[e];
+                    if (y2 != NIL) {
+                        const unsigned char* cp = a.codes + (size_t)y2 * a.code_stride;
+                        prefetch_l2(cp);
+                        if (((uintptr_t)cp & 127) + a.code_stride > 128) prefetch_l2(cp + 128 - ((uintptr_t)cp & 127));
+                        prefetch_l2(&r.gvis[(y2 * 2654435761u) >> (32 - r.gv_bits)]);
+                    }
+                }
+        }
+    }
     c.hop++;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -227,13 +258,13 @@ __device__ inline void rq_reseed(SearchCtx& c, RqCtx& r) {
     __syncthreads();
 }
 
-template <bool GLOBAL_VIS>
+template <bool GLOBAL_VIS, int W>
 __device__ inline void rq_layer_search(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, int layer, int ef, int (*s_cnt)[4], int* s_pred) {
     while (true) {
         int best = *c.s_best, len = *c.s_len;
         if (best >= len) break;
         uint64_t ckey = c.A[best];
-        rq_expand<GLOBAL_VIS>(G, c, a, r, key_id(ckey), layer, ef, best, s_cnt, s_pred);
+        rq_expand<GLOBAL_VIS, W>(G, c, a, r, key_id(ckey), layer, ef, best, s_cnt, s_pred);
         if (*c.s_nadmit == 0) {
             // nothing admitted (the common case once the list is full): the list only loses the expanded flag of `best`, and the
             // next candidate is the first unexpanded entry after it -- the one the prefetching warp has just located.
@@ -249,8 +280,10 @@ __device__ inline void rq_layer_search(const GraphDev& G, SearchCtx& c, const Se
     }
 }
 
-template <int NG>
-__global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, GraphDev G, SearchArgs a) {
+// W warps per CTA: 8 (4 CTAs per SM, 592 queries resident) or 4 (7 CTAs per SM: a batch of 1024 is resident at once -- the walk is
+// bound by the ~1 000 dependent hops of a query, so queries in flight, not warps per query, set the throughput).
+template <int NG, int W = HS_WARPS>
+__global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_kernel(VecDev V, GraphDev G, SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ints[8];
     __shared__ unsigned int s_work;
@@ -315,11 +348,11 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, Gr
         __syncthreads();
         for (int layer = (int)G.entry_layer; layer > 0; --layer) {   // search.rs:321-327: one best node per upper layer
             rq_reseed<false>(c, r);
-            rq_layer_search<false>(G, c, a, r, layer, 1, s_cnt, &s_pred);
+            rq_layer_search<false, W>(G, c, a, r, layer, 1, s_cnt, &s_pred);
             __syncthreads();
         }
         rq_reseed<true>(c, r);
-        rq_layer_search<true>(G, c, a, r, 0, a.last_k, s_cnt, &s_pred);             // search.rs:335-345
+        rq_layer_search<true, W>(G, c, a, r, 0, a.last_k, s_cnt, &s_pred);             // search.rs:335-345
         __syncthreads();
 
         c.s_ntodo = &s_ints[3]; c.s_nadmit = &s_ints[6];   // rq_expand pointed both at its counter slot; closest_up_nodes (hs_expand) needs two
@@ -355,7 +388,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, Gr
             }
             __syncthreads();
             int total = s_total;
-            for (int s = warp; s < total; s += HS_WARPS) {                  // exact similarities (Dot) of the survivors
+            for (int s = warp; s < total; s += W) {                         // exact similarities (Dot) of the survivors
                 float ab = warp_dot_t<NG>(reinterpret_cast<const float4*>(V.vecs + (size_t)surv_id[s] * V.ld), reinterpret_cast<const float4*>(c.qvec), ng, lane);
                 if (lane == 0) { surv_real[s] = ab; c.n_dist++; }
             }
@@ -387,7 +420,7 @@ __global__ void __launch_bounds__(HS_THREADS, 4) hnsw_rabitq_kernel(VecDev V, Gr
             if (threadIdx.x == 0) *c.s_len = hlen;
             __syncthreads();
         }
-        hs_emit_results<NG>(V, G, c, a, q);
+        hs_emit_results<NG, W>(V, G, c, a, q);
     }
     if (lane == 0 && c.n_dist) atomicAdd(&a.counters[0], c.n_dist);
     if (threadIdx.x == 0) {

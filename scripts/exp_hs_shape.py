@@ -28,9 +28,9 @@ del vecs
 seg.build_hnsw(seed=2, max_batch=8192)
 torch.cuda.synchronize()
 gt = {b: seg.search(qs[b][0], k, method=_lib.NIDX_METHOD_BRUTE)[0].cpu().numpy() for b in qs}
-configs = [("8", "0", 1024, "0"), ("8", "0", 1024, "1"), ("8", "0", 592, "1"), ("8", "0", 1184, "1"), ("8", "0", 1184, "0")]
-for w, bits, b, pair in configs:
-    os.environ["NIDX_B200_HS_W"], os.environ["NIDX_B200_HS_W4_BITS"], os.environ["NIDX_B200_HS_PAIR"] = w, bits, pair
+configs = [("8", "0", 1024, "0", "0"), ("8", "0", 1024, "0", "512"), ("8", "0", 1024, "0", "544"), ("8", "0", 1024, "0", "0")]
+for w, bits, b, pair, grid in configs:
+    os.environ["NIDX_B200_HS_W"], os.environ["NIDX_B200_HS_W4_BITS"], os.environ["NIDX_B200_HS_PAIR"], os.environ["NIDX_B200_HS_GRID"] = w, bits, pair, grid
     out = (torch.empty((b, k), dtype=torch.int32, device=dev), torch.empty((b, k), dtype=torch.float32, device=dev), torch.empty((b,), dtype=torch.int32, device=dev))
     for i in range(3):
         seg.search(qs[b][i], k, ef=ef, method=_lib.NIDX_METHOD_HNSW, out=out)
@@ -44,5 +44,5 @@ for w, bits, b, pair in configs:
     ms = e0.elapsed_time(e1) / 12
     ids = seg.search(qs[b][0], k, ef=ef, method=_lib.NIDX_METHOD_HNSW)[0].cpu().numpy()
     c = seg.counters()
-    print(json.dumps({"pair": pair, "warps": w, "hash_bits": bits, "batch": b, "ms": ms, "qps": b / ms * 1e3, "kernel_ms": seg.last_kernel_ms(), "recall": B.recall_at_k(ids, gt[b]),
+    print(json.dumps({"grid": grid, "pair": pair, "warps": w, "hash_bits": bits, "batch": b, "ms": ms, "qps": b / ms * 1e3, "kernel_ms": seg.last_kernel_ms(), "recall": B.recall_at_k(ids, gt[b]),
                       "overflows": c["overflows"], "sims_per_q": c["similarities"] / b}), flush=True)
