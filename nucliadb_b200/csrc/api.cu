@@ -1193,6 +1193,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         a.hash_bits = hash_bits; a.list_cap = list_cap; a.cu_cap = cu_cap;
         a.codes = s->d_quant; a.code_stride = s->quant_stride; a.planes = planes; a.qparams = params;
         a.gvisited = w.scores.as<uint32_t>(); a.gv_bits = gv_bits; a.last_k = last_k;
+        { const char* ep = getenv("NIDX_B200_RQ_PREFETCH"); a.rq_prefetch = ep ? atoi(ep) : 1; }
         ENSURE(w.sched, 64);
         a.work_counter = w.sched.as<unsigned int>();
         a.counters = s->d_counters;

@@ -393,14 +393,18 @@ __global__ void __launch_bounds__(BM_THREADS, 3) bm25_kernel(TxtDev T, Bm25Args 
             }
             __syncthreads();
             // ---- phase C: score and accumulate by rank ----
+            // All of a thread's postings are scored and added first (independent chains: the loads of the bitmap word, the rank
+            // base, the weight and the norm entry of different postings overlap); which adds crossed the threshold is kept in a
+            // per-thread mask and the candidates are appended afterwards -- a warp vote per posting only where some lane has one
+            // (rare once the top-k threshold is established).
             for (int round = 0; round < nrounds; ++round) {
                 if (!one_round) load_round(round);
+                uint32_t cmask = 0;
+                uint32_t cds[BM_PT];
 #pragma unroll
                 for (int u = 0; u < BM_PT; ++u) {
-                    bool act = actm & (1u << u);
-                    bool crossed = false;
-                    uint32_t cd = 0;
-                    if (act) {
+                    cds[u] = 0;
+                    if (actm & (1u << u)) {
                         uint32_t off = pd[u].x - lo, tfn = pd[u].y;
                         uint32_t wd = bitmap[off >> 5];
                         uint32_t rank = (uint32_t)base[off >> 5] + __popc(wd & ((1u << (off & 31)) - 1u));
@@ -411,20 +415,28 @@ __global__ void __launch_bounds__(BM_THREADS, 3) bm25_kernel(TxtDev T, Bm25Args 
                         uint32_t fx = (uint32_t)__float2uint_rn(__fmul_rn(wgt, frac));
                         if (fx == 0) fx = 1;
                         uint32_t oldv = atomicAdd(&acc[rank], fx);
+                        bool crossed;
                         if (CONJ) {
                             uint32_t oldw = atomicAdd(&cnts[rank >> 2], 1u << (8 * (rank & 3)));   // byte counter (nt <= 128) inside its 32-bit word
                             crossed = (int)(((oldw >> (8 * (rank & 3))) & 0xFFu) + 1) == nt;       // the posting that completes the conjunction hands the document on
                         } else {
                             crossed = oldv < thr_fx && oldv + fx >= thr_fx;
                         }
-                        cd = (rank << 17) | off;
+                        cds[u] = (rank << 17) | off;
+                        if (crossed) cmask |= 1u << u;
                     }
-                    unsigned mk = __ballot_sync(0xFFFFFFFFu, crossed);
-                    if (mk) {
-                        int basepos = 0;
-                        if (lane == 0) basepos = atomicAdd(&s_ncand, __popc(mk));
-                        basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
-                        if (crossed) cand[basepos + __popc(mk & ((1u << lane) - 1))] = cd;
+                }
+                if (__any_sync(0xFFFFFFFFu, cmask != 0)) {
+#pragma unroll
+                    for (int u = 0; u < BM_PT; ++u) {
+                        const bool crossed = (cmask >> u) & 1u;
+                        unsigned mk = __ballot_sync(0xFFFFFFFFu, crossed);
+                        if (mk) {
+                            int basepos = 0;
+                            if (lane == 0) basepos = atomicAdd(&s_ncand, __popc(mk));
+                            basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+                            if (crossed) cand[basepos + __popc(mk & ((1u << lane) - 1))] = cds[u];
+                        }
                     }
                 }
             }

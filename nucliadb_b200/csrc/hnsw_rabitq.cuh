@@ -25,13 +25,15 @@
 namespace nidx {
 
 constexpr int RQ_RC = 64;   // rerank chunk
+constexpr int RQ_TCH = 16;  // code chunks (16 bytes) whose query-plane words are kept transposed in shared memory (d <= 1984)
 
 __host__ __device__ __forceinline__ size_t rq_smem_bytes(int ld, int d, int list_cap, int hash_bits, int k) {
-    return hs_smem_bytes(ld, list_cap, hash_bits) + (size_t)4 * (d / 32) * 4 + (size_t)RQ_RC * 12 + (size_t)(k + 1) * 8 + 64;
+    return hs_smem_bytes(ld, list_cap, hash_bits) + (size_t)4 * (d / 32) * 4 + (size_t)RQ_TCH * 64 + (size_t)RQ_RC * 12 + (size_t)(k + 1) * 8 + 64 + 16;
 }
 
 struct RqCtx {
     const uint32_t* planes;   // shared memory, [4][nw]
+    const uint32_t* planes_t; // shared memory, [RQ_TCH][4 planes][4 words]: plane words by code chunk (16-byte aligned)
     int nw;
     float low, delta, root_dim;
     uint32_t sum_quantized;
@@ -57,6 +59,15 @@ __device__ __forceinline__ void rq_finish(const RqCtx& r, uint32_t idot, uint32_
 
 // weighted popcount of one 16-byte chunk of a code against the four query bit planes (words -2, -1 of chunk 0 are the header)
 __device__ __forceinline__ uint32_t rq_chunk_dot(const RqCtx& r, int ch, uint4 w) {
+    if (ch < RQ_TCH) {   // the four planes' words that face this chunk, contiguous (zero where the chunk holds the header or padding)
+        const uint4* pt = reinterpret_cast<const uint4*>(r.planes_t) + ch * 4;
+        const uint4 p0 = pt[0], p1 = pt[1], p2 = pt[2], p3 = pt[3];
+        uint32_t d0 = __popc(p0.x & w.x) + __popc(p0.y & w.y) + __popc(p0.z & w.z) + __popc(p0.w & w.w);
+        uint32_t d1 = __popc(p1.x & w.x) + __popc(p1.y & w.y) + __popc(p1.z & w.z) + __popc(p1.w & w.w);
+        uint32_t d2 = __popc(p2.x & w.x) + __popc(p2.y & w.y) + __popc(p2.z & w.z) + __popc(p2.w & w.w);
+        uint32_t d3 = __popc(p3.x & w.x) + __popc(p3.y & w.y) + __popc(p3.z & w.z) + __popc(p3.w & w.w);
+        return d0 + d1 * 2 + d2 * 4 + d3 * 8;
+    }
     uint32_t ws[4] = {w.x, w.y, w.z, w.w};
     uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
@@ -106,6 +117,7 @@ template <bool GLOBAL_VIS, int W>
 __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, uint32_t node, int layer, int ef, int best,
                                  int (*s_cnt)[4], int* s_pred) {
     constexpr int NPG = W * 4;     // neighbours per pass: eight lanes each
+    constexpr int NP = W >= 8 ? 1 : 2;   // passes in flight together: one adjacency row of 32 per iteration
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7;
     const int stride = G.stride(layer);
@@ -137,14 +149,15 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
     const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
     const bool hit = c.pref_node[cur] == node;
     const uint32_t* row = G.row(node, layer);
-    for (int e0 = 0; e0 < stride; e0 += 2 * NPG) {
+    for (int e0 = 0; e0 < stride; e0 += NP * NPG) {
         // two passes at once: every global request of both (codes, visited-set CAS) is in flight before anything is consumed
-        uint32_t y[2];
-        uint4 w0[2], w1[2];
-        bool valid[2], fresh[2] = {false, false}, ov = false;
-        const uint4* c4[2];
+        uint32_t y[NP];
+        uint4 w0[NP], w1[NP];
+        bool valid[NP], fresh[NP], ov = false;
+        const uint4* c4[NP];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < NP; ++p) {
+            fresh[p] = false;
             const int e = e0 + p * NPG + (int)(threadIdx.x >> 3);
             y[p] = NIL;
             if (e < stride) y[p] = hit ? prow[e] : __ldg(row + e);
@@ -157,7 +170,7 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
             }
         }
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < NP; ++p) {
             if (GLOBAL_VIS) {
                 if (valid[p] && sub == 0) {
                     if (visited >= r.gv_limit) ov = true;
@@ -181,7 +194,7 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
             }
         }
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < NP; ++p) {
             uint32_t idot = 0;
             if (valid[p] && (GLOBAL_VIS || fresh[p])) {
                 if (sub < nchunks) idot += rq_chunk_dot(r, sub, w0[p]);
@@ -204,7 +217,7 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
     }
     if (warp == W - 1) {
         cp_async_commit_wait_all();
-        if (GLOBAL_VIS) {
+        if (GLOBAL_VIS && a.rq_prefetch) {
             // The predicted next node's adjacency row is in shared memory now: pull its neighbours' codes and visited-table slots
             // into L2 while this hop's merge runs (3.6 KB + 32 lines per hop; wasted when the prediction fails).
             __syncwarp();
@@ -303,6 +316,8 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_ker
     c.pref_node = reinterpret_cast<uint32_t*>(p); p += 16;
     uint64_t* heap = reinterpret_cast<uint64_t*>(p); p += (size_t)(a.k + 1) * 8;          // rerank_top's `best`, rank keys, descending
     uint32_t* planes = reinterpret_cast<uint32_t*>(p); p += (size_t)4 * (V.d / 32) * 4;
+    p = smem + (((size_t)(p - smem) + 15) & ~(size_t)15);
+    uint32_t* planes_t = reinterpret_cast<uint32_t*>(p); p += (size_t)RQ_TCH * 64;
     uint32_t* surv_id = reinterpret_cast<uint32_t*>(p); p += RQ_RC * 4;
     float* surv_up = reinterpret_cast<float*>(p); p += RQ_RC * 4;
     float* surv_real = reinterpret_cast<float*>(p);
@@ -314,7 +329,7 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_ker
     c.hash_limit = (int)((15u << a.hash_bits) >> 4) - HS_MAX_ROW;
     c.n_dist = c.n_expand = c.n_overflow = 0;
     c.qnorm = 0.0f;
-    r.planes = planes; r.nw = V.d / 32; r.root_dim = __fsqrt_rn((float)V.d);
+    r.planes = planes; r.planes_t = planes_t; r.nw = V.d / 32; r.root_dim = __fsqrt_rn((float)V.d);
     r.gvis = a.gvisited + ((size_t)blockIdx.x << a.gv_bits);
     r.gv_bits = a.gv_bits; r.gv_mask = (1u << a.gv_bits) - 1; r.gv_limit = (int)((15u << a.gv_bits) >> 4) - HS_MAX_ROW;
     r.n_quant = r.n_rerank = 0;
@@ -331,6 +346,10 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_ker
         const float* qsrc = a.queries + (size_t)q * V.ld;
         for (int i = threadIdx.x; i < ng; i += blockDim.x) reinterpret_cast<float4*>(c.qvec)[i] = reinterpret_cast<const float4*>(qsrc)[i];
         for (int i = threadIdx.x; i < 4 * r.nw; i += blockDim.x) planes[i] = a.planes[(size_t)q * 4 * r.nw + i];
+        for (int i = threadIdx.x; i < RQ_TCH * 16; i += blockDim.x) {      // [chunk][plane][t]: word 4 * chunk - 2 + t of the plane
+            int ch = i >> 4, kpl = (i >> 2) & 3, wi = ch * 4 + (i & 3) - 2;
+            planes_t[i] = (wi >= 0 && wi < r.nw) ? a.planes[(size_t)q * 4 * r.nw + kpl * r.nw + wi] : 0u;
+        }
         if (threadIdx.x < 8) s_cnt[threadIdx.x >> 2][threadIdx.x & 3] = 0;   // closest_up's hops (hs_expand) change the parity between queries
         RabitqQueryParams qp = qparams[q];
         r.low = qp.low; r.delta = qp.delta; r.sum_quantized = qp.sum_quantized;

@@ -60,6 +60,7 @@ struct SearchArgs {
     uint32_t* gvisited;               // [grid][1 << gv_bits] layer-0 visited table in global memory (L2)
     int gv_bits;
     int last_k;                       // min(k * RERANKING_FACTOR, RERANKING_LIMIT)
+    int rq_prefetch;                  // pull the predicted next node's neighbour codes / visited slots into L2
 };
 
 struct SearchCtx {
@@ -209,6 +210,7 @@ template <bool CU>
 __device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
     int len = *c.s_len, ntodo = *c.s_ntodo;
     int first = CU ? 1 : 0;
+    int my_best = INT_MAX;
     for (int t = threadIdx.x; t < len - first + ntodo; t += blockDim.x) {
         uint64_t key;
         int p;
@@ -234,9 +236,12 @@ __device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
         }
         if (p < cap) {
             c.B[p] = key;
-            if (key & 1ull) atomicMin(c.s_best_next, p);
+            if (key & 1ull) my_best = min(my_best, p);
         }
     }
+    // first unexpanded entry of the merged list: one shared-memory atomic per warp, not per entry
+    my_best = __reduce_min_sync(0xFFFFFFFFu, my_best);
+    if ((threadIdx.x & 31) == 0 && my_best != INT_MAX) atomicMin(c.s_best_next, my_best);
     __syncthreads();
     if (threadIdx.x == 0) {
         int nl = len - first + *c.s_nadmit;

@@ -21,8 +21,8 @@ seg.build_hnsw(seed=2, max_batch=8192)
 seg.rabitq_encode()
 gt = seg.search(queries[0], k, method=_lib.NIDX_METHOD_BRUTE)[0].cpu().numpy()
 out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq,), dtype=torch.int32, device=dev))
-for bits, rqw in (("", "8"), ("", "4"), ("17", "4"), ("17", "8")):
-    os.environ["NIDX_B200_RQ_W"] = rqw
+for bits, rqw, pf in (("", "8", "1"), ("", "8", "0"), ("", "4", "1"), ("", "4", "0"), ("17", "4", "0")):
+    os.environ["NIDX_B200_RQ_W"], os.environ["NIDX_B200_RQ_PREFETCH"] = rqw, pf
     if bits:
         os.environ["NIDX_B200_RQ_VISITED_BITS"] = bits
     times = []
@@ -32,5 +32,5 @@ for bits, rqw in (("", "8"), ("", "4"), ("17", "4"), ("17", "8")):
         times.append(round(seg.last_kernel_ms(), 3))
     seg.search(queries[0], k, method=_lib.NIDX_METHOD_HNSW_RABITQ, out=out)
     c = seg.counters_ex()
-    print(json.dumps({"warps": rqw, "visited_bits": bits or "default(16)", "kernel_ms": times, "recall": recall_at_k(out[0].cpu().numpy(), gt), "overflows": c["overflows"],
+    print(json.dumps({"prefetch": pf, "warps": rqw, "visited_bits": bits or "default(16)", "kernel_ms": times, "recall": recall_at_k(out[0].cpu().numpy(), gt), "overflows": c["overflows"],
                       "estimates_per_q": c["estimates"] / nq, "expansions_per_q": c["expansions"] / nq}), flush=True)
