@@ -32,6 +32,14 @@ def peaks():
         return {}
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the committed ncu capture of this exact workload (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def timed(fn, steps, warmup):
     import torch
 
@@ -77,16 +85,18 @@ def bench_scan(args):
         cpu_dt = time.perf_counter() - t0
         pk = float(peaks().get("hbm_gbs", 6650.0))
         ach = alg / (kms * 1e-3) / 1e9
-        if qq.shape[0] >= 128:   # tensor-core path: 3 TF32 MMAs per product; TF32 dense peak = half the measured bf16 peak
-            tf = 3 * 2.0 * n * d * qq.shape[0] / (kms * 1e-3) / 1e12
+        wl = f"nidx_vector brute-force cosine top-10, {n}x{d} f32, {label}"
+        if qq.shape[0] >= 128:   # tensor-core filter: ONE TF32 pass over Q x N (2 N d Q flops); TF32 dense peak = half the measured bf16 peak
+            tf = 2.0 * n * d * qq.shape[0] / (kms * 1e-3) / 1e12
             tpk = float(peaks().get("bf16_tflops", 1590.0)) / 2
-            roof = {"bound": "tensor", "achieved": tf, "peak": tpk, "unit": "TFLOP/s", "frac": tf / tpk, "kernel": "scan_scores_tc_kernel", "kernel_ms": kms,
-                    "traffic": None, "note": "3xTF32 MMA flops; peak = MEASURED_PEAKS bf16_tflops / 2 (TF32 runs at half the bf16 rate)"}
+            roof = {"bound": "tensor", "achieved": tf, "peak": tpk, "unit": "TFLOP/s", "frac": tf / tpk, "kernel": "scan_tc_filter_kernel", "kernel_ms": kms,
+                    "traffic": ncu_traffic(wl), "note": "2 N d Q flops of the single TF32 pass / the filter kernel's time; peak = MEASURED_PEAKS bf16_tflops / 2 "
+                    "(TF32 runs at half the bf16 rate); the exact refine of the survivors is in ms_per_step, not here"}
         else:
-            roof = {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "scan_scores_kernel_t", "kernel_ms": kms, "traffic": None}
+            roof = {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "scan_scores_kernel_t", "kernel_ms": kms, "traffic": ncu_traffic(wl)}
         lines.append({"metric": "exact k-NN QPS (brute force)", "value": qq.shape[0] / (ms * 1e-3), "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"nidx_vector brute-force cosine top-10, {n}x{d} f32, {label}", "passes_over_block": passes},
+                      "config": {"workload": wl, "passes_over_block": passes},
                       "parity": {"ids_identical_to_oracle": bool((ids == oi).all()), "max_abs_score_diff": float(np.abs(sc - os_).max())},
                       "roofline": roof,
                       "cpu_baseline": {"value": min(qq.shape[0], 256) / cpu_dt, "unit": "queries/s", "cores": effective_cores(), "kind": "port",
@@ -260,7 +270,9 @@ def bench_bm25(args):
                       "config": {"workload": f"BM25 {n_docs} docs / {nterms}-term queries, top-{k}, {name}", "vocab": n_terms, "postings": int(c['term_off'][-1]),
                                  "postings_per_query": postings / nq, "setup_seconds": t_setup},
                       "parity": {"counts_identical_to_oracle": ok_counts, "max_rel_score_diff": rel, "ids_identical_fraction": same_ids, "sample": ns},
-                      "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "bm25_kernel", "kernel_ms": kms, "traffic": None,
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "kernel": "bm25_kernel", "kernel_ms": kms,
+                                   "traffic": ncu_traffic(f"BM25 {n_docs} docs / {nterms}-term queries, top-{k}, {name}"),
+                                   "parity_note": "BM25 parity is UNPINNED: the oracle restates tantivy 0.26's published formula, tantivy itself is not in the tree",
                                    "alg_bytes_note": "postings x (8 with tf, 4 + 1 for tf == 1: SURVEY 8d); the records read are 8 B either way"},
                       "cpu_baseline": {"value": ns / cpu_dt, "unit": "queries/s", "cores": effective_cores(), "kind": "port", "sample": f"{ns} queries"},
                       "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(qt_h.nbytes + qo_h.nbytes), "d2h_bytes_per_step": nq * k * 8 + nq * 12}})

@@ -200,7 +200,8 @@ int nidx_merge_topk(int32_t device, const uint32_t* ids, const float* scores, in
                     uint32_t* out_ids, float* out_scores, int32_t* out_part, void* stream);
 
 /* Counters of the last HNSW search / build on this segment (for the roofline accounting,
- * SURVEY 8d): [0] similarity evaluations, [1] node expansions, [2] visited-set overflows. */
+ * SURVEY 8d): [0] similarity evaluations, [1] node expansions, [2] visited-set overflows.  Every search call counts into its
+ * own workspace, so concurrent searches never mix their counts; "last" = the call that was issued last. */
 int nidx_vec_counters(nidx_vec_segment* seg, uint64_t out[3]);
 /* The same with the quantised walk's: [0] exact similarities computed, [1] expansions, [2] visited-set overflows, [3] closest_up
  * overflows, [4] RaBitQ estimates, [5] exact similarities the sequential rerank_top needed (<= the share of [0] spent there). */

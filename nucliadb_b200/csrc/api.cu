@@ -162,7 +162,9 @@ struct nidx_vec_segment {
     std::mutex map_mu;
     unsigned char* d_quant = nullptr;   // RaBitQ codes [n][quant_stride] (vectors.quant records, padded)
     int quant_stride = 0;
-    unsigned long long* d_counters = nullptr;  // [4]
+    unsigned long long* d_counters = nullptr;  // [8] the build's counters
+    std::atomic<unsigned long long*> last_counters{nullptr};   // counters of the LAST search call (they live in that call's workspace: concurrent
+                                                               // searches never add into each other's), read by nidx_vec_counters*
     unsigned int* d_work_counter = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the dominant kernel of the last search (bench roofline)
     WorkspacePool pool;
@@ -535,7 +537,8 @@ int nidx_vec_counters_ex(nidx_vec_segment* s, uint64_t out[6]) {
     if (!s || !out) return fail(NIDX_EINVAL, "null argument");
     CU(cudaSetDevice(s->cfg.device));
     unsigned long long h[8];
-    CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    unsigned long long* src = s->last_counters.load();
+    CU(cudaMemcpy(h, src ? src : s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 6; ++i) out[i] = h[i];
     return 0;
 }
@@ -544,7 +547,8 @@ int nidx_vec_counters(nidx_vec_segment* s, uint64_t out[3]) {
     if (!s) return fail(NIDX_EINVAL, "null segment");
     CU(cudaSetDevice(s->cfg.device));
     unsigned long long h[4];
-    CU(cudaMemcpy(h, s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    unsigned long long* src = s->last_counters.load();
+    CU(cudaMemcpy(h, src ? src : s->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2] + h[3];
     return 0;
 }
@@ -755,7 +759,9 @@ static int hnsw_search_smem(const nidx_vec_segment* s, int ef0, int k, int* list
     // (search.rs:205-216), each adding at most one adjacency row of pending candidates.
     int cu = std::min(std::max(ef0 + k * s->s0, 2 * ef0), 4096);
     int lc = std::max(ef0, cu);
-    int slots = next_pow2(std::max(2048, (ef0 * s->s0 * 3) / 2));
+    // visited-set slots: a walk visits about ef0 * s0 * 0.6 nodes on easy data and up to ~1.3x that on clustered data at small ef
+    // (10 M x 768, 4096 centres, ef = 30: 13 of 1024 queries overflowed 2048 slots): at least 4096, 1.5 x ef0 x s0 above that
+    int slots = next_pow2(std::max(4096, (ef0 * s->s0 * 3) / 2));
     slots = std::max(slots, next_pow2(4 * lc));
     *list_cap = lc; *cu_cap = cu; *hash_bits = ilog2(slots);
     *bytes = hs_smem_bytes(s->ld, lc, *hash_bits);
@@ -1075,14 +1081,16 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         int slots = std::max(1, std::min(grid / n_qblocks, n_chunks));   // CTAs per query block; 1 when there are more blocks than CTAs
         size_t cand_n = (size_t)nq * slots * TC2_L;
         ENSURE(w.scores, cand_n * 8 + 64);
-        ENSURE(w.sched, 64);
+        ENSURE(w.sched, 128);
+        unsigned long long* call_counters = reinterpret_cast<unsigned long long*>(w.sched.as<unsigned char>() + 64);
         Tc2Args ta;
         ta.nq = nq; ta.n_qblocks = n_qblocks; ta.n_chunks = n_chunks; ta.slots = slots; ta.qnorms = w.qnorms.as<float>(); ta.bits = bits;
         ta.cand_score = w.scores.as<float>(); ta.cand_id = reinterpret_cast<uint32_t*>(w.scores.as<float>() + cand_n);
         ta.work_counter = w.sched.as<unsigned int>();
         CU(cudaFuncSetAttribute(scan_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
         grid = n_qblocks <= grid ? n_qblocks * slots : grid;
-        CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        CU(cudaMemsetAsync(w.sched.p, 0, 128, stream));
+        s->last_counters.store(call_counters);
         CU(cudaEventRecord(s->ev_k0, stream));
         scan_tc_filter_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, stream>>>(map_q, s->map_v, V, ta);
         CU(cudaEventRecord(s->ev_k1, stream));
@@ -1091,7 +1099,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         size_t smem_rf = tc2_refine_smem(s->ld, cap);
         if (smem_rf > 48 * 1024) CU(cudaFuncSetAttribute(scan_tc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rf));
         scan_tc_refine_kernel<<<nq, 256, smem_rf, stream>>>(V, dq, w.qnorms.as<float>(), slots, ta.cand_score, ta.cand_id, bits, s->max_norm, p->min_score, k, cap,
-                                                            d_ids, d_sc, d_cnt, s->d_counters + 6);
+                                                            d_ids, d_sc, d_cnt, call_counters + 6);
         LAUNCHED();
         CU(cudaGetLastError());
     } else if (method == NIDX_METHOD_BRUTE) {
@@ -1194,11 +1202,11 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         a.codes = s->d_quant; a.code_stride = s->quant_stride; a.planes = planes; a.qparams = params;
         a.gvisited = w.scores.as<uint32_t>(); a.gv_bits = gv_bits; a.last_k = last_k;
         { const char* ep = getenv("NIDX_B200_RQ_PREFETCH"); a.rq_prefetch = ep ? atoi(ep) : 1; }
-        ENSURE(w.sched, 64);
+        ENSURE(w.sched, 128);
         a.work_counter = w.sched.as<unsigned int>();
-        a.counters = s->d_counters;
-        CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
-        CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        a.counters = reinterpret_cast<unsigned long long*>(w.sched.as<unsigned char>() + 64);   // per call, in the call's workspace
+        CU(cudaMemsetAsync(a.work_counter, 0, 128, stream));
+        s->last_counters.store(a.counters);
         CU(cudaEventRecord(s->ev_k0, stream));
         kern<<<grid, threads, smem, stream>>>(V, s->gdev(), a);
         CU(cudaEventRecord(s->ev_k1, stream));
@@ -1218,11 +1226,11 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         a.out_ids = d_ids; a.out_scores = d_sc; a.out_counts = d_cnt;
         a.hash_bits = hash_bits; a.list_cap = list_cap; a.cu_cap = cu_cap;
         // the scheduler counter lives in the workspace: concurrent calls must not share it
-        ENSURE(w.sched, 64);
+        ENSURE(w.sched, 128);
         a.work_counter = w.sched.as<unsigned int>();
-        a.counters = s->d_counters;
-        CU(cudaMemsetAsync(a.work_counter, 0, 4, stream));
-        CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        a.counters = reinterpret_cast<unsigned long long*>(w.sched.as<unsigned char>() + 64);   // per call, in the call's workspace
+        CU(cudaMemsetAsync(a.work_counter, 0, 128, stream));
+        s->last_counters.store(a.counters);
         hs_kernel_t kern = pick_search_kernel(s->ld);
         int threads = HS_THREADS;
         // Shape: 8 warps per query, 4 CTAs per SM -- or 4 warps with two rows in flight each, 7 CTAs per SM, when that lets the
@@ -1456,6 +1464,7 @@ static int run_insertions(nidx_vec_segment* s, const std::vector<uint8_t>& level
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_rev, reverse_link_kernel, HB_THREADS, smem_rev));
         int rev_grid = std::max(1, occ_rev) * s->sm_count;
         CU(cudaMemsetAsync(s->d_counters, 0, 8 * sizeof(unsigned long long), stream));
+        s->last_counters.store(nullptr);   // the getters report the build's counters until the next search
 
 
         VecDev V = s->vdev();

@@ -81,23 +81,63 @@ __device__ inline int select_neighbours_heuristic(const VecDev& V, HeurSmem& h, 
     __syncthreads();
     int nsel = 0;
     if (PRELOAD) {
-        for (int i = warp; i < nc; i += HB_WARPS) {   // one warp per candidate row: 3 KB coalesced
+        for (int i = warp; i < nc; i += HB_WARPS) {   // one warp per candidate row: 3 KB coalesced, asynchronous (the rows of a warp overlap)
             const float4* src = reinterpret_cast<const float4*>(V.vecs + (size_t)h.cand_id[i] * V.ld);
             float4* dst = reinterpret_cast<float4*>(h.cache + (size_t)i * V.ld);
-            for (int g = lane; g < ng; g += 32) dst[g] = ldg_stream(src + g);
+            for (int g = lane; g < ng; g += 32) cp_async16(dst + g, src + g);
         }
+        cp_async_commit_wait_all();
         __syncthreads();
-        int npairs = nc * (nc - 1) / 2;
-        for (int p = warp; p < npairs; p += HB_WARPS) {   // pair p = (i, j), j < i
-            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-            while (i * (i - 1) / 2 > p) --i;
-            while ((i + 1) * i / 2 <= p) ++i;
-            int j = p - i * (i - 1) / 2;
-            float ab = warp_dot_ss(reinterpret_cast<const float4*>(h.cache + (size_t)i * V.ld), reinterpret_cast<const float4*>(h.cache + (size_t)j * V.ld), ng, lane);
-            if (lane == 0) {
-                float s = sim_from_parts(V.sim, ab, V.norms[h.cand_id[i]], V.norms[h.cand_id[j]]);
-                h.pair[i * HB_PAIR_LD + j] = s;
-                h.pair[j * HB_PAIR_LD + i] = s;
+        // All pairwise similarities, register tiled: a warp takes a 4 x 4 block of (i, j) pairs, loads the eight rows' float4 groups
+        // once per group and keeps the 16 pairs' four accumulators in registers -- a quarter of the shared-memory reads of one
+        // dot per pair (the phase is bound by shared-memory bandwidth: 33 x 32 / 2 pairs x 6 KB).  Per pair the arithmetic is
+        // exactly warp_dot_ss's (lane-blocked groups in increasing order, four FMA accumulators, the same butterfly): bit-identical.
+        {
+            const int nb = (nc + 3) >> 2;                 // blocks of four rows
+            const int nblk = nb * (nb + 1) / 2;           // block pairs (ib >= jb)
+            for (int bp = warp; bp < nblk; bp += HB_WARPS) {
+                int ib = (int)((sqrtf(1.0f + 8.0f * (float)bp) - 1.0f) * 0.5f);
+                while (ib * (ib + 1) / 2 > bp) --ib;
+                while ((ib + 1) * (ib + 2) / 2 <= bp) ++ib;
+                const int jb = bp - ib * (ib + 1) / 2;
+                float acc[4][4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) { acc[r][c2][0] = 0.f; acc[r][c2][1] = 0.f; acc[r][c2][2] = 0.f; acc[r][c2][3] = 0.f; }
+                const float4* rows_i[4];
+                const float4* rows_j[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    rows_i[r] = reinterpret_cast<const float4*>(h.cache + (size_t)min(ib * 4 + r, nc - 1) * V.ld);
+                    rows_j[r] = reinterpret_cast<const float4*>(h.cache + (size_t)min(jb * 4 + r, nc - 1) * V.ld);
+                }
+                for (int g = lane; g < ng; g += 32) {
+                    float4 va[4], vb[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { va[r] = rows_i[r][g]; vb[r] = rows_j[r][g]; }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) {
+                            acc[r][c2][0] = __fmaf_rn(va[r].x, vb[c2].x, acc[r][c2][0]);
+                            acc[r][c2][1] = __fmaf_rn(va[r].y, vb[c2].y, acc[r][c2][1]);
+                            acc[r][c2][2] = __fmaf_rn(va[r].z, vb[c2].z, acc[r][c2][2]);
+                            acc[r][c2][3] = __fmaf_rn(va[r].w, vb[c2].w, acc[r][c2][3]);
+                        }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c2 = 0; c2 < 4; ++c2) {
+                        const int i = ib * 4 + r, j = jb * 4 + c2;
+                        float ab = butterfly_sum(__fadd_rn(__fadd_rn(acc[r][c2][0], acc[r][c2][1]), __fadd_rn(acc[r][c2][2], acc[r][c2][3])));
+                        if (lane == 0 && i < nc && j < i) {
+                            float sv = sim_from_parts(V.sim, ab, V.norms[h.cand_id[i]], V.norms[h.cand_id[j]]);
+                            h.pair[i * HB_PAIR_LD + j] = sv;
+                            h.pair[j * HB_PAIR_LD + i] = sv;
+                        }
+                    }
             }
         }
         __syncthreads();

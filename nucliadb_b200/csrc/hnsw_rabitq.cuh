@@ -115,7 +115,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 template <bool GLOBAL_VIS, int W>
 __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, uint32_t node, int layer, int ef, int best,
-                                 int (*s_cnt)[4], int* s_pred) {
+                                 int (*s_cnt)[4], int* s_pred, unsigned long long* s_maxtodo) {
     constexpr int NPG = W * 4;     // neighbours per pass: eight lanes each
     constexpr int NP = W >= 8 ? 1 : 2;   // passes in flight together: one adjacency row of 32 per iteration
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -125,6 +125,7 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
     int* cnt = s_cnt[cur];
     c.s_ntodo = cnt;        // hs_merge reads the number of todo keys and of admitted keys: both = cnt[0]
     c.s_nadmit = cnt;
+    c.s_maxtodo = &s_maxtodo[cur];
     const int len = *c.s_len;
     const uint64_t wkey = len >= ef ? c.A[len - 1] : 0;
     const int visited = *c.s_hash_count;       // stable during the expansion (thread 0 updates it after the barrier)
@@ -208,7 +209,10 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
                 float est, err;
                 rq_finish(r, idot, w0[p].x, w0[p].y, est, err);       // chunk 0 starts with the code's header (dot_quant_original, sum_bits)
                 uint64_t key = make_key(est, y[p], 1);
-                if (key > wkey) c.todo_key[atomicAdd(&cnt[0], 1)] = key;   // layer_search (search.rs:286): better than the worst of a full list
+                if (key > wkey) {                                             // layer_search (search.rs:286): better than the worst of a full list
+                    c.todo_key[atomicAdd(&cnt[0], 1)] = key;
+                    atomicMax(c.s_maxtodo, (unsigned long long)key);
+                }
             }
             unsigned mf = __ballot_sync(0xFFFFFFFFu, sub == 0 && fresh[p]);
             if (lane == 0 && mf) atomicAdd(&cnt[1], __popc(mf));
@@ -243,6 +247,7 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
         if (cnt[2]) c.n_overflow++;
         int* nxt = s_cnt[cur ^ 1u];
         nxt[0] = 0; nxt[1] = 0; nxt[2] = 0;
+        s_maxtodo[cur ^ 1u] = 0;
     }
 }
 
@@ -272,12 +277,12 @@ __device__ inline void rq_reseed(SearchCtx& c, RqCtx& r) {
 }
 
 template <bool GLOBAL_VIS, int W>
-__device__ inline void rq_layer_search(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, int layer, int ef, int (*s_cnt)[4], int* s_pred) {
+__device__ inline void rq_layer_search(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, int layer, int ef, int (*s_cnt)[4], int* s_pred, unsigned long long* s_maxtodo) {
     while (true) {
         int best = *c.s_best, len = *c.s_len;
         if (best >= len) break;
         uint64_t ckey = c.A[best];
-        rq_expand<GLOBAL_VIS, W>(G, c, a, r, key_id(ckey), layer, ef, best, s_cnt, s_pred);
+        rq_expand<GLOBAL_VIS, W>(G, c, a, r, key_id(ckey), layer, ef, best, s_cnt, s_pred, s_maxtodo);
         if (*c.s_nadmit == 0) {
             // nothing admitted (the common case once the list is full): the list only loses the expanded flag of `best`, and the
             // next candidate is the first unexpanded entry after it -- the one the prefetching warp has just located.
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_ker
     __shared__ unsigned int s_work;
     __shared__ int s_wtot[RQ_RC / 32], s_total, s_hlen;
     __shared__ int s_cnt[2][4], s_pred;
+    __shared__ unsigned long long s_maxtodo[2], s_maxtodo_cu;
     __shared__ float s_best_k;
     SearchCtx c;
     RqCtx r;
@@ -351,6 +357,7 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_ker
             planes_t[i] = (wi >= 0 && wi < r.nw) ? a.planes[(size_t)q * 4 * r.nw + kpl * r.nw + wi] : 0u;
         }
         if (threadIdx.x < 8) s_cnt[threadIdx.x >> 2][threadIdx.x & 3] = 0;   // closest_up's hops (hs_expand) change the parity between queries
+        if (threadIdx.x < 2) s_maxtodo[threadIdx.x] = 0;
         RabitqQueryParams qp = qparams[q];
         r.low = qp.low; r.delta = qp.delta; r.sum_quantized = qp.sum_quantized;
         __syncthreads();
@@ -367,14 +374,15 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_ker
         __syncthreads();
         for (int layer = (int)G.entry_layer; layer > 0; --layer) {   // search.rs:321-327: one best node per upper layer
             rq_reseed<false>(c, r);
-            rq_layer_search<false, W>(G, c, a, r, layer, 1, s_cnt, &s_pred);
+            rq_layer_search<false, W>(G, c, a, r, layer, 1, s_cnt, &s_pred, s_maxtodo);
             __syncthreads();
         }
         rq_reseed<true>(c, r);
-        rq_layer_search<true, W>(G, c, a, r, 0, a.last_k, s_cnt, &s_pred);             // search.rs:335-345
+        rq_layer_search<true, W>(G, c, a, r, 0, a.last_k, s_cnt, &s_pred, s_maxtodo);             // search.rs:335-345
         __syncthreads();
 
         c.s_ntodo = &s_ints[3]; c.s_nadmit = &s_ints[6];   // rq_expand pointed both at its counter slot; closest_up_nodes (hs_expand) needs two
+        c.s_maxtodo = &s_maxtodo_cu;
         // ---- rerank_top (rabitq.rs:222-244) over the list, best estimate first ----
         const int len = *c.s_len;
         if (threadIdx.x == 0) { s_hlen = 0; s_best_k = 0.0f; }

@@ -72,6 +72,7 @@ struct SearchCtx {
     uint32_t* pref_row;   // [2][HS_MAX_ROW] speculatively prefetched adjacency rows (double buffered by hop parity)
     uint32_t* pref_node;  // [2] node each buffer belongs to (NIL = none)
     int *s_len, *s_best, *s_best_next, *s_ntodo, *s_hash_count, *s_flag, *s_nadmit;
+    unsigned long long* s_maxtodo;   // the largest admitted key of the expansion: list entries above it keep their position
     unsigned hop;
     uint32_t hash_mask;
     int hash_bits, hash_limit;
@@ -144,6 +145,7 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
             *c.s_hash_count += ntodo;
             *c.s_best_next = INT_MAX;
             *c.s_nadmit = 0;
+            *c.s_maxtodo = 0;
             c.n_expand++;
         }
     } else if (warp == W - 1) {
@@ -176,7 +178,7 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
         uint64_t key = make_key(s, y, 1);
         bool admit = CU ? (s >= min_score) : (key > wkey);
         c.todo_key[j] = admit ? key : 0;
-        if (admit) atomicAdd(c.s_nadmit, 1);
+        if (admit) { atomicAdd(c.s_nadmit, 1); atomicMax(c.s_maxtodo, (unsigned long long)key); }
         c.n_dist++;
     };
     if constexpr (PAIR) {   // two rows in flight per warp (fewer warps per query, more queries per SM)
@@ -211,6 +213,7 @@ __device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
     int len = *c.s_len, ntodo = *c.s_ntodo;
     int first = CU ? 1 : 0;
     int my_best = INT_MAX;
+    const uint64_t maxtodo = *c.s_maxtodo;
     for (int t = threadIdx.x; t < len - first + ntodo; t += blockDim.x) {
         uint64_t key;
         int p;
@@ -219,7 +222,8 @@ __device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
             key = c.A[i];
             if (!CU && i == best) key &= ~1ull;  // the entry just expanded
             int shift = 0;
-            for (int j = 0; j < ntodo; ++j) shift += (c.todo_key[j] > key);
+            if (key < maxtodo)                      // entries above every admitted key keep their position
+                for (int j = 0; j < ntodo; ++j) shift += (c.todo_key[j] > key);
             p = t + shift;
         } else {
             int j = t - (len - first);
@@ -362,6 +366,7 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_search_ker
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_ints[8];
     __shared__ unsigned int s_work;
+    __shared__ unsigned long long s_maxtodo;
     SearchCtx c;
     unsigned char* p = smem;
     c.qvec = reinterpret_cast<float*>(p); p += (size_t)V.ld * 4;
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_search_ker
     c.hop = 0;
     c.s_len = &s_ints[0]; c.s_best = &s_ints[1]; c.s_best_next = &s_ints[2]; c.s_ntodo = &s_ints[3];
     c.s_hash_count = &s_ints[4]; c.s_flag = &s_ints[5]; c.s_nadmit = &s_ints[6];
+    c.s_maxtodo = &s_maxtodo;
     c.hash_bits = a.hash_bits;
     c.hash_mask = (1u << a.hash_bits) - 1;
     c.hash_limit = (int)((15u << a.hash_bits) >> 4) - HS_MAX_ROW;

@@ -68,10 +68,13 @@ def _oracle_graph(seg, n, m, m0):
     return og
 
 
+@pytest.mark.parametrize("shape", ["8", "4"])
 @pytest.mark.parametrize("d,n", [(128, 20000), (768, 6000)])
-def test_quantised_walk_matches_oracle(d, n):
+def test_quantised_walk_matches_oracle(d, n, shape, monkeypatch):
     """hnsw/search.rs:306-383 with a RaBitQ query: ids, scores and the number of estimates / expansions equal the oracle's
-    restatement on the same graph (oracle.hnsw_search_rabitq), with and without deletions, duplicates suppression and min_score."""
+    restatement on the same graph (oracle.hnsw_search_rabitq), with and without deletions, duplicates suppression and min_score --
+    for both CTA shapes of the kernel (8 warps per query; 4 warps, which large batches take)."""
+    monkeypatch.setenv("NIDX_B200_RQ_W", shape)
     v = make_vectors(n, d, seed=61)
     v[100:110] = v[90:100]                                   # byte-identical vectors for with_duplicates=False
     q = make_queries(v, 24)

@@ -47,7 +47,11 @@ def test_brute_force_min_score_and_alive():
     assert all(alive[i] for i in ids[ids != 0xFFFFFFFF])
 
 
-def test_hnsw_search_matches_oracle_on_oracle_graph(small_data):
+@pytest.mark.parametrize("shape", ["8", "4"])
+def test_hnsw_search_matches_oracle_on_oracle_graph(small_data, shape, monkeypatch):
+    """Both CTA shapes of hnsw_search_kernel (8 warps per query, the default; 4 warps with two rows in flight each) walk exactly
+    like the oracle."""
+    monkeypatch.setenv("NIDX_B200_HS_W", shape)
     v, q = small_data
     g = O.hnsw_build(v, M=16, M0=32, efC=100, max_batch=64, nthreads=8)
     seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=100)
