@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(BM_THREADS, 3) bm25_kernel(TxtDev T, Bm25Args 
         int mn = INT_MAX, tot = 0;
 #pragma unroll
         for (int j = 0; j < BM_TPL; ++j) {
+            if (32 * j >= nt) break;            // (uniform) a 50-term query needs two of the four term groups
             int i = lane + 32 * j;
             uint32_t len = 0;
             if (i < nt) {

@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_rabitq_ker
     float* surv_real = reinterpret_cast<float*>(p);
     c.hop = 0;
     c.s_len = &s_ints[0]; c.s_best = &s_ints[1]; c.s_best_next = &s_ints[2]; c.s_ntodo = &s_ints[3];
+    c.s_bn = &s_ints[2];   // (the lean layer search of hnsw_search.cuh is not used by this kernel)
     c.s_hash_count = &s_ints[4]; c.s_flag = &s_ints[5]; c.s_nadmit = &s_ints[6];
     c.hash_bits = a.hash_bits;
     c.hash_mask = (1u << a.hash_bits) - 1;

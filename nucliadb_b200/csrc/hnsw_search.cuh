@@ -72,6 +72,7 @@ struct SearchCtx {
     uint32_t* pref_row;   // [2][HS_MAX_ROW] speculatively prefetched adjacency rows (double buffered by hop parity)
     uint32_t* pref_node;  // [2] node each buffer belongs to (NIL = none)
     int *s_len, *s_best, *s_best_next, *s_ntodo, *s_hash_count, *s_flag, *s_nadmit;
+    int* s_bn;                       // [2] parity slots for s_best_next in the barrier-lean layer search
     unsigned long long* s_maxtodo;   // the largest admitted key of the expansion: list entries above it keep their position
     unsigned hop;
     uint32_t hash_mask;
@@ -120,11 +121,14 @@ __device__ inline void hs_reseed(SearchCtx& c) {
 // Speculation: while warp 0 works, the last warp starts an asynchronous copy (cp.async) of the adjacency
 // row of the node that will be expanded next if no new neighbour outranks it -- `pred_idx` in the list --
 // into the other half of a double buffer; the row's HBM latency then overlaps this expansion's vector loads.
-template <bool CU, int NG, int W = HS_WARPS, bool PAIR = false>
-__device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& c, uint32_t node, int layer, int ef, float min_score, int best) {
+// LEAN (the layer search's hot loop): the list length arrives in a register and s_best_next alternates between two slots, so that
+// hs_merge needs no barrier after thread 0 has published the new length -- three barriers per expansion instead of four.
+template <bool CU, int NG, int W = HS_WARPS, bool PAIR = false, bool LEAN = false>
+__device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& c, uint32_t node, int layer, int ef, float min_score, int best, int len_in = -1) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int stride = G.stride(layer);
     unsigned cur = c.hop & 1u;
+    if (LEAN) c.s_best_next = c.s_bn + cur;
     if (warp == 0) {
         const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
         bool hit = c.pref_node[cur] == node;
@@ -149,7 +153,7 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
             c.n_expand++;
         }
     } else if (warp == W - 1) {
-        int len = *c.s_len;
+        int len = LEAN ? len_in : *c.s_len;
         int pred = -1;
         if (CU) {
             pred = len > 1 ? 1 : -1;
@@ -170,7 +174,7 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
         if (lane == 0) c.pref_node[cur ^ 1u] = pnode;
     }
     __syncthreads();
-    int ntodo = *c.s_ntodo, len = *c.s_len;
+    int ntodo = *c.s_ntodo, len = LEAN ? len_in : *c.s_len;
     uint64_t wkey = (!CU && len >= ef) ? c.A[len - 1] : 0;
     int ng = V.ld >> 2;
     auto finish = [&](int j, uint32_t y, float ab, float vnorm) {
@@ -181,6 +185,16 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
         if (admit) { atomicAdd(c.s_nadmit, 1); atomicMax(c.s_maxtodo, (unsigned long long)key); }
         c.n_dist++;
     };
+    // A warp's later rows (j + W, j + 2W, ...) are pulled into L2 while it works on its first one: their loads then cost an L2
+    // hit instead of a second and third HBM round trip on the expansion's critical path (one prefetch per 128-byte line, a lane
+    // each; no registers held, unlike a second row in flight).
+    if (!PAIR) {
+        const int lines = (V.ld * 4 + 127) >> 7;
+        for (int j = warp + W; j < ntodo; j += W) {
+            const char* rowp = reinterpret_cast<const char*>(V.vecs + (size_t)c.todo_id[j] * V.ld);
+            for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(rowp + (size_t)l * 128));
+        }
+    }
     if constexpr (PAIR) {   // two rows in flight per warp (fewer warps per query, more queries per SM)
         for (int j = warp; j < ntodo; j += 2 * W) {
             uint32_t y0 = c.todo_id[j];
@@ -208,12 +222,16 @@ __device__ inline void hs_expand(const VecDev& V, const GraphDev& G, SearchCtx& 
 
 // Merge the admitted todo keys into the sorted list A -> B (rank merge, no sort), keep at most `cap`.
 // CU: entry 0 (the popped candidate) is dropped.  Afterwards A/B are swapped and s_len/s_best updated.
-template <bool CU>
-__device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
-    int len = *c.s_len, ntodo = *c.s_ntodo;
+// LEAN: `len_io` / `best_io` carry the list length and the next candidate in registers (every thread computes them); no barrier
+// after thread 0's update of the shared copies, which only code outside the hot loop reads (after a barrier of its own).
+template <bool CU, bool LEAN = false>
+__device__ inline void hs_merge(SearchCtx& c, int cap, int best, int* len_io = nullptr, int* best_io = nullptr) {
+    int len = LEAN ? *len_io : *c.s_len, ntodo = *c.s_ntodo;
     int first = CU ? 1 : 0;
     int my_best = INT_MAX;
     const uint64_t maxtodo = *c.s_maxtodo;
+    const int nadmit = *c.s_nadmit;         // final since hs_expand's last barrier; re-zeroed by the next expansion
+    int* const bn = c.s_best_next;
     for (int t = threadIdx.x; t < len - first + ntodo; t += blockDim.x) {
         uint64_t key;
         int p;
@@ -245,28 +263,32 @@ __device__ inline void hs_merge(SearchCtx& c, int cap, int best) {
     }
     // first unexpanded entry of the merged list: one shared-memory atomic per warp, not per entry
     my_best = __reduce_min_sync(0xFFFFFFFFu, my_best);
-    if ((threadIdx.x & 31) == 0 && my_best != INT_MAX) atomicMin(c.s_best_next, my_best);
+    if ((threadIdx.x & 31) == 0 && my_best != INT_MAX) atomicMin(bn, my_best);
     __syncthreads();
+    int nl = len - first + nadmit;
+    const bool over = nl > cap;
+    if (over) nl = cap;
+    const int nb = *bn;
     if (threadIdx.x == 0) {
-        int nl = len - first + *c.s_nadmit;
-        if (nl > cap) { nl = cap; if (CU) c.n_overflow += (1ull << 32); }
+        if (over && CU) c.n_overflow += (1ull << 32);
         *c.s_len = nl;
-        *c.s_best = *c.s_best_next;
+        *c.s_best = nb;
     }
     uint64_t* t = c.A; c.A = c.B; c.B = t;
-    __syncthreads();
+    if (LEAN) { *len_io = nl; *best_io = nb; }
+    else __syncthreads();
 }
 
 // hnsw/search.rs:242-304 on the list held in shared memory.
 template <int NG, int W = HS_WARPS, bool PAIR = false>
 __device__ inline void hs_layer_search(const VecDev& V, const GraphDev& G, SearchCtx& c, int layer, int ef) {
-    while (true) {
-        int best = *c.s_best, len = *c.s_len;
-        if (best >= len) break;
+    int best = *c.s_best, len = *c.s_len;     // published by hs_reseed (behind its barrier); from here on in registers
+    while (best < len) {
         uint64_t ckey = c.A[best];
-        hs_expand<false, NG, W, PAIR>(V, G, c, key_id(ckey), layer, ef, 0.0f, best);
-        hs_merge<false>(c, ef, best);
+        hs_expand<false, NG, W, PAIR, true>(V, G, c, key_id(ckey), layer, ef, 0.0f, best, len);
+        hs_merge<false, true>(c, ef, best, &len, &best);
     }
+    c.s_best_next = c.s_bn;                    // (callers that use the shared copies come after a barrier)
 }
 
 // NodeFilter::passes (search.rs:147-170) for the popped candidate; warp 0 only, result broadcast by the caller.
@@ -367,7 +389,9 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_search_ker
     __shared__ int s_ints[8];
     __shared__ unsigned int s_work;
     __shared__ unsigned long long s_maxtodo;
+    __shared__ int s_bn[2];
     SearchCtx c;
+    c.s_bn = s_bn;
     unsigned char* p = smem;
     c.qvec = reinterpret_cast<float*>(p); p += (size_t)V.ld * 4;
     c.A = reinterpret_cast<uint64_t*>(p); p += (size_t)a.list_cap * 8;
@@ -378,7 +402,7 @@ __global__ void __launch_bounds__(W * 32, W == HS_WARPS ? 4 : 7) hnsw_search_ker
     c.pref_row = reinterpret_cast<uint32_t*>(p); p += 2 * HS_MAX_ROW * 4;
     c.pref_node = reinterpret_cast<uint32_t*>(p);
     c.hop = 0;
-    c.s_len = &s_ints[0]; c.s_best = &s_ints[1]; c.s_best_next = &s_ints[2]; c.s_ntodo = &s_ints[3];
+    c.s_len = &s_ints[0]; c.s_best = &s_ints[1]; c.s_best_next = &s_bn[0]; c.s_ntodo = &s_ints[3];
     c.s_hash_count = &s_ints[4]; c.s_flag = &s_ints[5]; c.s_nadmit = &s_ints[6];
     c.s_maxtodo = &s_maxtodo;
     c.hash_bits = a.hash_bits;
