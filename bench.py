@@ -142,6 +142,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.sm, self.max_sm, self.reasons, self._stop, self._t = index, [], None, set(), threading.Event(), None
+        self.power, self.power_limit = [], None
         self.nv = None
         try:
             import pynvml
@@ -150,6 +151,10 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                pass
         except Exception:
             self.nv = None
 
@@ -172,6 +177,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
@@ -195,7 +204,8 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "source": "nvml" if self.nv is not None else "unavailable"}
+                "samples": len(self.sm), "source": "nvml" if self.nv is not None else "unavailable",
+                "power_w": float(np.median(self.power)) if self.power else None, "power_limit_w": self.power_limit}
 
 
 def effective_cores() -> int:

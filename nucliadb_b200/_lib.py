@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnidx_b200.so")
+# NIDX_B200_LIB names another build of the same library next to this file (kernel-shape experiments: scripts/exp_*.py)
+LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("NIDX_B200_LIB", "libnidx_b200.so")))
 
 NIDX_MEM_HOST, NIDX_MEM_DEVICE = 0, 1
 NIDX_SIM_DOT, NIDX_SIM_COSINE, NIDX_SIM_L2 = 0, 1, 2

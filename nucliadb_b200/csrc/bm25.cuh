@@ -38,13 +38,21 @@
 
 namespace nidx {
 
-constexpr int BM_THREADS = 256;
+// CTA shape: threads x posting slots per thread = 4096 slots per round; CTAs per SM (launch bounds).  512 x 8 x 2 (64 registers,
+// 32 warps per SM) measured against 256 x 16 x 3 (80 registers, 24 warps per SM) on 5 M documents: OR-50 338 k vs 335 k QPS,
+// AND-3 1.32 M vs 1.21 M; same outputs (make EXTRA="-DBM_THREADS_CFG=256 -DBM_PT_CFG=16 -DBM_MINB_CFG=3" builds the other one).
+#ifndef BM_THREADS_CFG
+#define BM_THREADS_CFG 512
+#define BM_PT_CFG 8
+#define BM_MINB_CFG 2
+#endif
+constexpr int BM_THREADS = BM_THREADS_CFG;
 constexpr int BM_WARPS = BM_THREADS / 32;
 constexpr int BM_MAX_TERMS = 128;
 constexpr int BM_TPL = BM_MAX_TERMS / 32;  // query terms per lane of the resolving warp
 constexpr int BM_FINE = 4096;              // skip-table granularity (documents)
 constexpr int BM_SKIP_DF = 256;            // terms with at least this many postings get a skip row
-constexpr int BM_PT = 16;                  // posting slots per thread and round (registers)
+constexpr int BM_PT = BM_PT_CFG;           // posting slots per thread and round (registers)
 constexpr int BM_SLOTS = BM_THREADS * BM_PT;   // 4096 posting slots per round
 constexpr int BM_OCT = BM_SLOTS / 8;       // 8-posting octets per round (one term each)
 constexpr int BM_MAX_SPAN = 32;            // fine tiles per tile at most: 131 072 documents, a 16 KB bitmap
@@ -119,7 +127,7 @@ __device__ __forceinline__ uint2 ldg_post(const uint2* p) {
 
 // CONJ: nidx_text (all terms must match).  TF: real term frequencies (else IndexRecordOption::Basic, tf == 1).
 template <bool CONJ, bool TF>
-__global__ void __launch_bounds__(BM_THREADS, 3) bm25_kernel(TxtDev T, Bm25Args a) {
+__global__ void __launch_bounds__(BM_THREADS, BM_MINB_CFG) bm25_kernel(TxtDev T, Bm25Args a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int tk_count;
     __shared__ uint64_t tk_thr;
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(BM_THREADS, 3) bm25_kernel(TxtDev T, Bm25Args 
             __syncthreads();
             // ---- phase S: rank base of every bitmap word (exclusive prefix popcount); Count collector ----
             {
-                constexpr int WPT = BM_WORDS / BM_THREADS;   // 16 consecutive words per thread, read twice (registers hold the postings)
+                constexpr int WPT = BM_WORDS / BM_THREADS;   // consecutive words per thread (a multiple of 8), read twice (registers hold the postings)
                 const int w0 = (int)threadIdx.x * WPT;
                 const bool mine = w0 < nwords;
                 uint32_t sum = 0;

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import NIL, RrfSource, ShardSearchRequest, ShardSearchResponse, TxtSearchParams, VecSearchParams, check, ptr
+from ._lib import RrfSource, ShardSearchRequest, ShardSearchResponse, TxtSearchParams, VecSearchParams, check, ptr
 
 KEYWORD, SEMANTIC, GRAPH = "keyword", "semantic", "graph"      # IndexSource (rank_fusion.py:54-57)
 _TYPE_BIT = {KEYWORD: 1, SEMANTIC: 2}

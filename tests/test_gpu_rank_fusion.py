@@ -11,7 +11,7 @@ from nucliadb_b200 import _lib
 from nucliadb_b200.rank_fusion import ReciprocalRankFusion, shard_search
 from nucliadb_b200.segment import TextSegment, VectorSegment
 from oracle.rank_fusion import rrf_fuse
-from test_rank_fusion import case_sources, load_cases, score_type
+from test_rank_fusion import load_cases
 
 pytestmark = pytest.mark.gpu
 

@@ -437,3 +437,25 @@ def test_normalize_vectors_matches_the_reference_fold():
     v = np.asarray([[3.0, 0.0, 4.0, 0.0]], dtype=np.float32)
     _lib.check(L.nidx_normalize_vectors(0, _lib.ptr(v), C.c_uint64(1), 4, 4, _lib.NIDX_MEM_HOST, None))
     assert v[0].tolist() == [np.float32(3.0) / np.float32(5.0), 0.0, np.float32(4.0) / np.float32(5.0), 0.0]
+
+
+def test_calls_on_alternating_streams_overlap_and_agree(small_data):
+    """One host thread, two streams, device buffers: every call gets a workspace that no call in flight is using (the pool
+    hands out one per stream), so the results equal the one-stream results whatever the interleaving."""
+    import torch
+
+    v, q = small_data
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=64)
+    seg.build_hnsw(seed=2, max_batch=256)
+    dq = [torch.from_numpy(np.roll(q, i, axis=0).copy()).cuda() for i in range(6)]
+    want = [tuple(t.clone() for t in seg.search(x, 10, ef=64, method=_lib.NIDX_METHOD_HNSW)) for x in dq]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    got = []
+    for rep in range(3):
+        for i, x in enumerate(dq):
+            with torch.cuda.stream(streams[i % 2]):
+                got.append((i, seg.search(x, 10, ef=64, method=_lib.NIDX_METHOD_HNSW)))
+    torch.cuda.synchronize()
+    for i, (ids, sc, cnt) in got:
+        assert torch.equal(ids, want[i][0]) and torch.equal(sc, want[i][1]) and torch.equal(cnt, want[i][2])
