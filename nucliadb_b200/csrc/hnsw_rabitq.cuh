@@ -101,8 +101,8 @@ __device__ __forceinline__ void rq_estimate(const RqCtx& r, const unsigned char*
     rq_finish(r, idot, dqo_bits, sum_bits, estimate, error);
 }
 
-// Expand `node` ranking by the estimate.  The whole CTA works on one adjacency row: EIGHT LANES PER NEIGHBOUR (32 neighbours per
-// pass of 256 threads).  Lane j of a group loads 16-byte chunk j (j + 8, ...) of the neighbour's code -- the 112 bytes of a
+// Expand `node` ranking by the estimate.  The whole CTA works on one adjacency row: EIGHT (8 warps) or FOUR (4 warps) LANES PER
+// NEIGHBOUR, 32 neighbours per pass.  Lane j of a group loads 16-byte chunk j (j + 8, ...) of the neighbour's code -- the 112 bytes of a
 // 768-d code arrive as seven adjacent 16-byte requests of one warp instruction -- and takes its weighted popcount; three
 // shuffles add the eight partial sums (integers: exact in any order).  The group's first lane tests the visited set (global
 // table: the atomicCAS and the code loads are in flight together, codes of visited neighbours are fetched for nothing) and
@@ -116,10 +116,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <bool GLOBAL_VIS, int W>
 __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchArgs& a, RqCtx& r, uint32_t node, int layer, int ef, int best,
                                  int (*s_cnt)[4], int* s_pred, unsigned long long* s_maxtodo) {
-    constexpr int NPG = W * 4;     // neighbours per pass: eight lanes each
-    constexpr int NP = W >= 8 ? 1 : 2;   // passes in flight together: one adjacency row of 32 per iteration
+    // LPN lanes per neighbour, so that the CTA covers one adjacency row of 32 per pass: 8 lanes (one 16-byte chunk each per 128 bytes
+    // of code) with 8 warps, 4 lanes (two chunks each) with 4 warps -- the float tail of the estimate then runs once per warp for
+    // eight neighbours instead of four.
+    constexpr int LPN = W >= 8 ? 8 : 4;
+    constexpr int CPL = 8 / LPN;         // chunks per lane and 128-byte block of code
+    constexpr int NPG = W * 32 / LPN;    // neighbours per pass (32)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane & 7;
+    const int sub = lane & (LPN - 1);
     const int stride = G.stride(layer);
     const unsigned cur = c.hop & 1u;
     int* cnt = s_cnt[cur];
@@ -150,73 +154,76 @@ __device__ inline void rq_expand(const GraphDev& G, SearchCtx& c, const SearchAr
     const uint32_t* prow = c.pref_row + cur * HS_MAX_ROW;
     const bool hit = c.pref_node[cur] == node;
     const uint32_t* row = G.row(node, layer);
-    for (int e0 = 0; e0 < stride; e0 += NP * NPG) {
-        // two passes at once: every global request of both (codes, visited-set CAS) is in flight before anything is consumed
-        uint32_t y[NP];
-        uint4 w0[NP], w1[NP];
-        bool valid[NP], fresh[NP], ov = false;
-        const uint4* c4[NP];
+    for (int e0 = 0; e0 < stride; e0 += NPG) {
+        // every global request of the pass (code chunks, visited-set CAS) is in flight before anything is consumed
+        const int e = e0 + (int)(threadIdx.x / LPN);
+        uint32_t y = NIL;
+        if (e < stride) y = hit ? prow[e] : __ldg(row + e);
+        const bool valid = y != NIL;
+        bool fresh = false, ov = false;
+        const uint4* c4 = reinterpret_cast<const uint4*>(a.codes + (size_t)(valid ? y : 0) * a.code_stride);
+        uint4 w[2][CPL];                 // the first 256 bytes of code (d <= 1984); longer codes loop below
+        auto load_chunks = [&]() {
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            fresh[p] = false;
-            const int e = e0 + p * NPG + (int)(threadIdx.x >> 3);
-            y[p] = NIL;
-            if (e < stride) y[p] = hit ? prow[e] : __ldg(row + e);
-            valid[p] = y[p] != NIL;
-            c4[p] = reinterpret_cast<const uint4*>(a.codes + (size_t)(valid[p] ? y[p] : 0) * a.code_stride);
-            w0[p] = make_uint4(0, 0, 0, 0); w1[p] = w0[p];
-            if (GLOBAL_VIS) {       // up to 256 bytes of code per neighbour here (d <= 1984); longer codes loop below
-                if (valid[p] && sub < nchunks) w0[p] = __ldg(c4[p] + sub);
-                if (valid[p] && sub + 8 < nchunks) w1[p] = __ldg(c4[p] + sub + 8);
-            }
-        }
+            for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            if (GLOBAL_VIS) {
-                if (valid[p] && sub == 0) {
-                    if (visited >= r.gv_limit) ov = true;
-                    else {
-                        uint32_t h = (y[p] * 2654435761u) >> (32 - r.gv_bits);
-                        while (true) {
-                            uint32_t old = atomicCAS(&r.gvis[h], NIL, y[p]);
-                            if (old == NIL) { fresh[p] = true; break; }
-                            if (old == y[p]) break;
-                            h = (h + 1) & r.gv_mask;
-                        }
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const int ch = blk * 8 + sub * CPL + cc;
+                    w[blk][cc] = ch < nchunks ? __ldg(c4 + ch) : make_uint4(0, 0, 0, 0);
+                }
+        };
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+            for (int cc = 0; cc < CPL; ++cc) w[blk][cc] = make_uint4(0, 0, 0, 0);
+        if (GLOBAL_VIS) {
+            if (valid) load_chunks();
+            if (valid && sub == 0) {
+                if (visited >= r.gv_limit) ov = true;
+                else {
+                    uint32_t h = (y * 2654435761u) >> (32 - r.gv_bits);
+                    while (true) {
+                        uint32_t old = atomicCAS(&r.gvis[h], NIL, y);
+                        if (old == NIL) { fresh = true; break; }
+                        if (old == y) break;
+                        h = (h + 1) & r.gv_mask;
                     }
                 }
-            } else {
-                if (valid[p] && sub == 0) fresh[p] = hash_insert(c, y[p], ov);
-                fresh[p] = __shfl_sync(0xFFFFFFFFu, fresh[p], lane & ~7);
-                if (fresh[p]) {
-                    if (sub < nchunks) w0[p] = __ldg(c4[p] + sub);
-                    if (sub + 8 < nchunks) w1[p] = __ldg(c4[p] + sub + 8);
-                }
             }
+        } else {
+            if (valid && sub == 0) fresh = hash_insert(c, y, ov);
+            fresh = __shfl_sync(0xFFFFFFFFu, fresh, lane & ~(LPN - 1));
+            if (fresh) load_chunks();
+        }
+        uint32_t idot = 0;
+        if (valid && (GLOBAL_VIS || fresh)) {
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const int ch = blk * 8 + sub * CPL + cc;
+                    if (ch < nchunks) idot += rq_chunk_dot(r, ch, w[blk][cc]);
+                }
+            for (int base = 16; base < nchunks; base += 8)
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const int ch = base + sub * CPL + cc;
+                    if (ch < nchunks) idot += rq_chunk_dot(r, ch, __ldg(c4 + ch));
+                }
         }
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            uint32_t idot = 0;
-            if (valid[p] && (GLOBAL_VIS || fresh[p])) {
-                if (sub < nchunks) idot += rq_chunk_dot(r, sub, w0[p]);
-                if (sub + 8 < nchunks) idot += rq_chunk_dot(r, sub + 8, w1[p]);
-                for (int ch = sub + 16; ch < nchunks; ch += 8) idot += rq_chunk_dot(r, ch, __ldg(c4[p] + ch));
+        for (int off = 1; off < LPN; off <<= 1) idot += __shfl_xor_sync(0xFFFFFFFFu, idot, off);
+        if (sub == 0 && fresh) {
+            float est, err;
+            rq_finish(r, idot, w[0][0].x, w[0][0].y, est, err);       // chunk 0 starts with the code's header (dot_quant_original, sum_bits)
+            uint64_t key = make_key(est, y, 1);
+            if (key > wkey) {                                             // layer_search (search.rs:286): better than the worst of a full list
+                c.todo_key[atomicAdd(&cnt[0], 1)] = key;
+                atomicMax(c.s_maxtodo, (unsigned long long)key);
             }
-            idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 1);
-            idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 2);
-            idot += __shfl_xor_sync(0xFFFFFFFFu, idot, 4);
-            if (sub == 0 && fresh[p]) {
-                float est, err;
-                rq_finish(r, idot, w0[p].x, w0[p].y, est, err);       // chunk 0 starts with the code's header (dot_quant_original, sum_bits)
-                uint64_t key = make_key(est, y[p], 1);
-                if (key > wkey) {                                             // layer_search (search.rs:286): better than the worst of a full list
-                    c.todo_key[atomicAdd(&cnt[0], 1)] = key;
-                    atomicMax(c.s_maxtodo, (unsigned long long)key);
-                }
-            }
-            unsigned mf = __ballot_sync(0xFFFFFFFFu, sub == 0 && fresh[p]);
-            if (lane == 0 && mf) atomicAdd(&cnt[1], __popc(mf));
         }
+        unsigned mf = __ballot_sync(0xFFFFFFFFu, sub == 0 && fresh);
+        if (lane == 0 && mf) atomicAdd(&cnt[1], __popc(mf));
         if (ov) cnt[2] = 1;
     }
     if (warp == W - 1) {

@@ -18,8 +18,7 @@ from . import _lib
 from ._lib import RrfSource, ShardSearchRequest, ShardSearchResponse, TxtSearchParams, VecSearchParams, check, ptr
 
 KEYWORD, SEMANTIC, GRAPH = "keyword", "semantic", "graph"      # IndexSource (rank_fusion.py:54-57)
-_TYPE_BIT = {KEYWORD: 1, SEMANTIC: 2}
-_TYPE_NAME = {0: "RELATION_RELEVANCE", 1: "BM25", 2: "VECTOR", 3: "BOTH"}
+_TYPE_OF = {KEYWORD: "BM25", SEMANTIC: "VECTOR", GRAPH: "RELATION_RELEVANCE"}      # SCORE_TYPE of a retriever's items
 
 
 class ReciprocalRankFusion:
@@ -54,13 +53,14 @@ class ReciprocalRankFusion:
         check(L.nidx_rank_fusion_rrf(C.c_int32(self.device), structs, C.c_int32(len(names)), C.c_int32(1), C.c_double(self._k), _lib.NIDX_MEM_HOST,
                                      ptr(out_keys), ptr(out_scores), ptr(out_refs), ptr(out_counts), None))
         fused = []
+        types = [_TYPE_OF.get(name, "RELATION_RELEVANCE") for name in names]
         for j in range(int(out_counts[0])):
-            mask = (int(out_refs[0, j]) >> 24) & 0xF
-            t = 0
-            for i, name in enumerate(names):
-                if mask >> i & 1:
-                    t |= _TYPE_BIT.get(name, 0)
-            fused.append((int(out_keys[0, j]), float(out_scores[0, j]), _TYPE_NAME[t]))
+            ref = int(out_refs[0, j])
+            first, mask = types[ref >> 28], (ref >> 24) & 0xF
+            joined = {t for i, t in enumerate(types) if mask >> i & 1}
+            # rank_fusion.py:166-174: the surviving (first) item becomes BOTH when a BM25 and a VECTOR item meet; other types are kept
+            st = "BOTH" if first in ("BM25", "VECTOR") and {"BM25", "VECTOR"} <= joined else first
+            fused.append((int(out_keys[0, j]), float(out_scores[0, j]), st))
         return fused
 
 

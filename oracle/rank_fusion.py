@@ -36,3 +36,11 @@ def rrf_fuse(sources, weights, k=60.0):
         merged = [(key, acc[key][0], acc[key][1], acc[key][2], acc[key][3]) for key in order]     # :178-184 (dict order = first insertion)
     merged.sort(key=lambda t: t[1], reverse=True)                                                 # :92-93 (stable)
     return merged
+
+
+def fused_score_type(first_type: str, types_of_contributors) -> str:
+    """rank_fusion.py:166-174: the surviving item (a key's first occurrence) becomes BOTH when a BM25 and a VECTOR item meet; an
+    item of any other type (RELATION_RELEVANCE) keeps its type whatever joins it."""
+    if first_type in ("BM25", "VECTOR") and {"BM25", "VECTOR"} <= set(types_of_contributors):
+        return "BOTH"
+    return first_type
