@@ -146,3 +146,22 @@ def test_vectors_quant_round_trip(tmp_path):
     (tmp_path / "vectors.quant").write_bytes(raw.tobytes()[:-3])
     with pytest.raises(_lib.NidxError):
         VectorSegment.open(str(tmp_path), d, similarity=_lib.NIDX_SIM_DOT, m=16, m0=32, ef_construction=64)
+
+
+@pytest.mark.parametrize("shape", ["8", "4"])
+def test_quantised_walk_with_the_reference_graph_constants(shape, monkeypatch):
+    """params.rs:34-46: M = 30, M0 = 60 (adjacency rows of 64 slots: two passes of 32 neighbours per expansion), efC = 100."""
+    monkeypatch.setenv("NIDX_B200_RQ_W", shape)
+    n, d = 8000, 256
+    v = make_vectors(n, d, seed=77)
+    q = make_queries(v, 16)
+    seg = VectorSegment.create(v, d, similarity=_lib.NIDX_SIM_DOT, m=30, m0=60, ef_construction=100)
+    seg.build_hnsw(seed=2, max_batch=512)
+    seg.rabitq_encode()
+    enc = O.rabitq_encode(v, nthreads=4)
+    og = _oracle_graph(seg, n, 30, 60)
+    ids, sc, cnt = seg.search(q, 10, method=_lib.NIDX_METHOD_HNSW_RABITQ)
+    c = seg.counters_ex()
+    oi, os_, oc, ocnt = O.hnsw_search_rabitq(v, enc, og, q, 10, nthreads=4)
+    assert (cnt == oc).all() and (ids == oi).all() and np.array_equal(sc, os_)
+    assert c["expansions"] == int(ocnt[1]) and c["overflows"] == 0
