@@ -1016,6 +1016,24 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
             bool scan_ok = walk_ok && !s->d_par_first && k <= 1024;
             if (use_hnsw_cost(s->n_par, matching, (size_t)k, (size_t)s->cfg.m, walk_ok)) method = walk_ok ? NIDX_METHOD_HNSW_RABITQ : NIDX_METHOD_HNSW;
             else method = scan_ok ? NIDX_METHOD_BRUTE_RABITQ : NIDX_METHOD_BRUTE;
+            // A walk keeps its list and visited set in shared memory: a very large top_k (the reference has no limit on it) does not
+            // fit one CTA.  AUTO then takes the exhaustive scan -- exact results -- instead of failing the request.
+            if (method == NIDX_METHOD_HNSW || method == NIDX_METHOD_HNSW_RABITQ) {
+                bool fits;
+                if (method == NIDX_METHOD_HNSW) {
+                    int ef = p->ef > 0 ? p->ef : s->cfg.ef_search;
+                    int cu = std::min(std::max(std::max(k, ef) + k * s->s0, 2 * std::max(k, ef)), 4096);
+                    int lcap = std::max(std::max(k, ef), cu);
+                    int slots = next_pow2(std::max(4096, (std::max(k, ef) * s->s0 * 3) / 2));
+                    slots = std::max(slots, next_pow2(4 * lcap));
+                    fits = hs_smem_bytes(s->ld, lcap, ilog2(slots)) <= 200 * 1024;
+                } else {
+                    int last_k = (int)std::min<size_t>((size_t)k * 100, 2000);
+                    int cu_cap = std::min(std::max(k + k * s->s0, 2 * k), 4096);
+                    fits = rq_smem_bytes(s->ld, s->d, std::max(last_k, cu_cap), ilog2(next_pow2(std::max(2048, 4 * cu_cap))), k) <= 200 * 1024;
+                }
+                if (!fits && k <= 1024) method = NIDX_METHOD_BRUTE;
+            }
         }
     }
     if ((method == NIDX_METHOD_HNSW || method == NIDX_METHOD_HNSW_RABITQ) && !s->has_graph) return fail(NIDX_ESTATE, "HNSW search requested but the segment has no graph");

@@ -459,3 +459,16 @@ def test_calls_on_alternating_streams_overlap_and_agree(small_data):
     torch.cuda.synchronize()
     for i, (ids, sc, cnt) in got:
         assert torch.equal(ids, want[i][0]) and torch.equal(sc, want[i][1]) and torch.equal(cnt, want[i][2])
+
+
+def test_auto_with_a_very_large_top_k_takes_the_exact_scan(small_data):
+    """The reference puts no limit on top_k; a walk for k = 700 would need more shared memory than a CTA has, so AUTO answers with
+    the exhaustive scan (exact results) instead of failing, while an explicit HNSW request reports the limit."""
+    v, q = small_data
+    seg = _seg(v, _lib.NIDX_SIM_COSINE, m=16, m0=32, ef_construction=64)
+    seg.build_hnsw(seed=2, max_batch=256)
+    ids, sc, cnt = seg.search(q[:4], 700, method=_lib.NIDX_METHOD_AUTO)
+    bi, bs, bc = seg.search(q[:4], 700, method=_lib.NIDX_METHOD_BRUTE)
+    assert (cnt == 700).all() and np.array_equal(ids, bi) and np.array_equal(sc, bs)
+    with pytest.raises(_lib.NidxError):
+        seg.search(q[:4], 700, method=_lib.NIDX_METHOD_HNSW)
