@@ -94,6 +94,28 @@ class EmulatedLib:
     def nidx_use_hnsw(self, total, matching, k, rq, m):
         return int(O.use_hnsw(_v(total), _v(matching), _v(k), has_rabitq=bool(_v(rq)), M=_v(m)))
 
+    def nidx_rank_fusion_rrf(self, device, sources, n_sources, nq, k, mem, out_keys, out_scores, out_refs, out_counts, stream):
+        """ReciprocalRankFusion.fuse through the oracle's restatement (host buffers), in the C ABI's output layout."""
+        from oracle.rank_fusion import rrf_fuse
+
+        n_sources, nq, kk = _v(n_sources), _v(nq), float(_v(k))
+        srcs = [sources[i] for i in range(n_sources)]
+        cap = sum(s.k for s in srcs)
+        ok, osc = _arr(out_keys, np.uint64, nq * cap).reshape(nq, cap), _arr(out_scores, np.float64, nq * cap).reshape(nq, cap)
+        orf, ocn = _arr(out_refs, np.uint32, nq * cap).reshape(nq, cap), _arr(out_counts, np.int32, nq)
+        for q in range(nq):
+            lists = []
+            for s in srcs:
+                keys = _arr(C.c_void_p(s.keys), np.uint64, nq * s.k).reshape(nq, s.k)[q]
+                scores = _arr(C.c_void_p(s.scores), np.float32, nq * s.k).reshape(nq, s.k)[q]
+                n = int(_arr(C.c_void_p(s.counts), np.int32, nq)[q]) if s.counts else int(np.sum(keys != np.uint64(0xFFFFFFFFFFFFFFFF)))
+                lists.append([(int(keys[j]), float(scores[j])) for j in range(n)])
+            fused = rrf_fuse(lists, [s.weight for s in srcs], k=kk)
+            ok[q], osc[q], orf[q], ocn[q] = np.uint64(0xFFFFFFFFFFFFFFFF), 0.0, NIL, len(fused)
+            for j, (key, sc, first, pos, mask) in enumerate(fused):
+                ok[q, j], osc[q, j], orf[q, j] = key, sc, (first << 28) | (mask << 24) | pos
+        return 0
+
     def nidx_normalize_vectors(self, device, vectors, n, d, ld, mem, stream):
         n, d, ld = _v(n), _v(d), _v(ld)
         a = np.ctypeslib.as_array(C.cast(vectors, C.POINTER(C.c_float)), shape=(n, ld))

@@ -3,6 +3,8 @@
 import json
 import os
 
+import numpy as np
+
 from oracle.rank_fusion import fused_score_type, rrf_fuse
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "rank_fusion.json")
@@ -37,3 +39,19 @@ def test_oracle_reproduces_the_reference_rank_fusion():
         seen_single += sum(1 for s in srcs if s) == 1
         seen_both += any(t == "BOTH" for _, _, t in c["fused"])
     assert seen_single >= 2 and seen_both >= 10
+
+
+def test_mirror_rank_fusion_on_the_emulated_abi(monkeypatch):
+    """The host mirror (nucliadb_b200/rank_fusion.py: sorting of the sources, packing for nidx_rank_fusion_rrf, score-type rule) against
+    the reference's outputs, on the oracle-backed emulation of the C ABI (no GPU: host-logic coverage only)."""
+    import abi_emulator
+    from nucliadb_b200 import _lib
+    from nucliadb_b200.rank_fusion import ReciprocalRankFusion
+
+    monkeypatch.setattr(_lib, "_lib", abi_emulator.EmulatedLib())
+    for c in load_cases():
+        got = ReciprocalRankFusion(k=c["k"], window=100, weights=c["weights"]).fuse({name: [(int(i), float(s)) for i, s in c[name]] for name in c["order"]})
+        single = sum(1 for name in c["order"] if c[name]) == 1
+        assert [[g[0], g[2]] for g in got] == [[w[0], w[2]] for w in c["fused"]]
+        want_scores = [float(np.float32(w[1])) if single else w[1] for w in c["fused"]]      # a skipped fusion reports the source's f32 scores
+        assert [g[1] for g in got] == want_scores
