@@ -719,15 +719,6 @@ static hs_kernel_t pick_rabitq_walk_kernel_w4(int ld) {
     return hnsw_rabitq_kernel<0, 4>;
 }
 
-static hs_kernel_t pick_search_kernel_w8pair(int ld) {
-    if (ld % 128 == 0) switch (ld / 128) {
-        case 3: return hnsw_search_kernel<3, 8, true>;
-        case 6: return hnsw_search_kernel<6, 8, true>;
-        default: break;
-    }
-    return nullptr;
-}
-
 static hs_kernel_t pick_rabitq_walk_kernel(int ld) {
     if (ld % 128 == 0) switch (ld / 128) {
         case 2: return hnsw_rabitq_kernel<2>;
@@ -1258,9 +1249,6 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
             const char* e2 = getenv("NIDX_B200_HS_W4_BITS");
             const int force_w = e1 ? atoi(e1) : 0, w4_bits = e2 ? atoi(e2) : 0;
             hs_kernel_t k4 = pick_search_kernel_w4(s->ld);
-            const char* e3 = getenv("NIDX_B200_HS_PAIR");
-            hs_kernel_t k8p = pick_search_kernel_w8pair(s->ld);
-            if (k8p && force_w != 4 && e3 && atoi(e3) == 1) kern = k8p;
             if (k4 && force_w == 4) {
                 int hb = w4_bits > 0 ? w4_bits : hash_bits;
                 size_t smem4 = hs_smem_bytes(s->ld, list_cap, hb);
@@ -1271,7 +1259,6 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         int grid = std::min(nq, std::max(1, occ) * s->sm_count);
-        if (const char* eg = getenv("NIDX_B200_HS_GRID")) { int gg = atoi(eg); if (gg > 0) grid = std::min(grid, gg); }
         CU(cudaEventRecord(s->ev_k0, stream));
         kern<<<grid, threads, smem, stream>>>(V, s->gdev(), a);
         CU(cudaEventRecord(s->ev_k1, stream));
