@@ -599,7 +599,14 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = float(np.mean(alg_bytes)) / (float(np.mean(kernel_ms)) * 1e-3) / 1e9
+    # The kernel's duration for the roofline comes from the TIMED REGION itself when it can: at N = 1 a step is memset + row norms
+    # (~5 us) + hnsw_search_kernel, so the median per-step device time is an upper bound of the kernel's launch duration under the
+    # very conditions the value was measured in (the separate accounting pass below the timed region runs after the CPU baseline
+    # and the extra measurements, and on power-capped boxes comes out slower than the timed steps).  The counters are those of the
+    # same query batches.  Multi-GPU steps contain the exchange, so they keep the accounting pass' kernel-only events.
+    kernel_ms_accounting = float(np.mean(kernel_ms))
+    kernel_ms_roof = kernel_ms_accounting if (multi or step_ms is None) else min(kernel_ms_accounting, step_ms["median"])
+    achieved = float(np.mean(alg_bytes)) / (kernel_ms_roof * 1e-3) / 1e9
     workload = f"HNSW search {n}x{d} cosine, ef={ef} k={k}, batch={nq}"
     traffic = None            # DRAM bytes per launch from the committed ncu capture of this exact workload, if there is one
     try:
@@ -766,7 +773,9 @@ def main():
             "build": {"workload": f"HNSW index build {n}x{d}, M={m} M0={m0} efC={args.efc}", "seconds": t_build, "vectors_per_s": n / t_build,
                       "similarities": build_counters["similarities"], "max_batch": args.max_batch, "data_seconds": t_data, **build_extra},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": "profiles/ncu_traffic.json" if traffic else None, "kernel": "hnsw_search_kernel", "kernel_ms": float(np.mean(kernel_ms)), "alg_bytes_per_launch": float(np.mean(alg_bytes)),
+                         "traffic_source": "profiles/ncu_traffic.json" if traffic else None, "kernel": "hnsw_search_kernel", "kernel_ms": kernel_ms_roof, "kernel_ms_accounting_pass": kernel_ms_accounting,
+                         "kernel_ms_source": "min(median device time of the timed steps (upper bound: includes memset + row norms), mean kernel-only time of the accounting pass)" if not multi else "kernel-only events of the accounting pass",
+                         "alg_bytes_per_launch": float(np.mean(alg_bytes)),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * (12 if use_lib else 8) + nq * 4, **e2e_mode},
