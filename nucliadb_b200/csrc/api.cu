@@ -1088,7 +1088,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         if (mr) return mr;
         int grid = std::min(n_chunks * n_qblocks, s->sm_count);
         int slots = std::max(1, std::min(grid / n_qblocks, n_chunks));   // CTAs per query block; 1 when there are more blocks than CTAs
-        size_t cand_n = (size_t)nq * slots * TC2_L;
+        size_t cand_n = (size_t)nq * slots * TC2_LISTS * TC2_L;
         ENSURE(w.scores, cand_n * 8 + 64);
         ENSURE(w.sched, 128);
         unsigned long long* call_counters = reinterpret_cast<unsigned long long*>(w.sched.as<unsigned char>() + 64);
@@ -1107,7 +1107,7 @@ static int vec_search_impl(nidx_vec_segment* s, const float* queries, int32_t nq
         int cap = topk_cap(k, 256);
         size_t smem_rf = tc2_refine_smem(s->ld, cap);
         if (smem_rf > 48 * 1024) CU(cudaFuncSetAttribute(scan_tc_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rf));
-        scan_tc_refine_kernel<<<nq, 256, smem_rf, stream>>>(V, dq, w.qnorms.as<float>(), slots, ta.cand_score, ta.cand_id, bits, s->max_norm, p->min_score, k, cap,
+        scan_tc_refine_kernel<<<nq, 256, smem_rf, stream>>>(V, dq, w.qnorms.as<float>(), slots * TC2_LISTS, ta.cand_score, ta.cand_id, bits, s->max_norm, p->min_score, k, cap,
                                                             d_ids, d_sc, d_cnt, call_counters + 6);
         LAUNCHED();
         CU(cudaGetLastError());

@@ -22,7 +22,8 @@
 //   warp 1   MMA issuer: one thread, tcgen05.mma.cta_group::1.kind::tf32, M = 128 (queries) x N = 256 (vectors) x K = 8,
 //            four per stage; tcgen05.commit releases the stage; accumulators double-buffered in TMEM (2 x 256 columns);
 //   warp 2   TMEM allocation;
-//   warps 4-7 epilogue: thread = query row = TMEM lane; tcgen05.ld 32 columns at a time, cosine scaling, eligibility bit,
+//   warps 4-11 epilogue: warp % 4 = TMEM lane quadrant, thread = query row; warps 4-7 read columns 0-127 of every tile, warps 8-11
+//            columns 128-255 (the read-out, not the tensor pipe, paces the kernel); tcgen05.ld 32 columns at a time, cosine scaling, eligibility bit,
 //            running top-L of the row in REGISTERS (unsorted + its minimum), fed through a per-row staging area in shared memory
 //            so that the (warp-wide) list update runs once per ~8-16 candidates of the busiest row, not once per column.
 // scan_tc_refine_kernel: one CTA per query: overflow test, tau, survivors, exact re-scoring (one warp per survivor),
@@ -44,11 +45,13 @@ constexpr int TC2_TILES = 8;          // vector tiles per chunk
 constexpr int TC2_CHUNK = TC2_N * TC2_TILES;   // 2048 vectors
 constexpr int TC2_L = 24;             // candidates kept per (query, chunk)
 constexpr int TC2_KMAX = 16;          // the filter path serves k <= TC2_KMAX
-constexpr int TC2_THREADS = 256;
+constexpr int TC2_EPI_WARPS = 8;      // epilogue warps: TMEM lane quadrant = warp % 4, column half of the tile = warp / 4
+constexpr int TC2_THREADS = (4 + TC2_EPI_WARPS) * 32;
 constexpr uint32_t TC2_A_BYTES = TC2_M * 128, TC2_B_BYTES = TC2_N * 128, TC2_STAGE_BYTES = TC2_A_BYTES + TC2_B_BYTES;
-constexpr int TC2_STAGE_ROWS = 16;    // staged candidates per query row between two merges into the register list
+constexpr int TC2_STAGE_ROWS = 12;    // staged candidates per (query row, column half) between two merges into the register list
+constexpr int TC2_LISTS = TC2_EPI_WARPS / 4;   // candidate lists per query row and CTA (one per column half)
 constexpr size_t TC2_SMEM_BYTES = 1024 /* alignment slack */ + (size_t)TC2_STAGES * TC2_STAGE_BYTES + 2 * TC2_N * 4 /* 1/|v| */ +
-                                  2 * (TC2_N / 32) * 4 /* eligibility */ + (size_t)TC2_STAGE_ROWS * TC2_M * 8 /* staging */ + 256;
+                                  2 * (TC2_N / 32) * 4 /* eligibility */ + (size_t)TC2_STAGE_ROWS * TC2_M * TC2_LISTS * 8 /* staging */ + 256;
 constexpr float TC2_EPS = 2.2e-3f;
 constexpr int TC2_SURV_CAP = 512;     // survivors per query the refine kernel re-scores; more => exact scan
 
@@ -75,8 +78,8 @@ struct Tc2Args {
     int nq, n_qblocks, n_chunks, slots;   // slots = CTAs per query block (1 when there are more query blocks than CTAs)
     const float* qnorms;          // [nq] (cosine)
     const uint64_t* bits;         // eligibility (alive & filter) per vector, or nullptr
-    float* cand_score;            // [nq][slots][TC2_L] approx scores, unsorted, -inf padded
-    uint32_t* cand_id;            // [nq][slots][TC2_L]
+    float* cand_score;            // [nq][slots * TC2_LISTS][TC2_L] approx scores, unsorted, -inf padded
+    uint32_t* cand_id;            // [nq][slots * TC2_LISTS][TC2_L]
     unsigned int* work_counter;
 };
 
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
     float* inv_vn = reinterpret_cast<float*>(smem + (size_t)TC2_STAGES * TC2_STAGE_BYTES);     // [2][256]
     uint32_t* elig = reinterpret_cast<uint32_t*>(inv_vn + 2 * TC2_N);                          // [2][8]
     float* stg_sc = reinterpret_cast<float*>(elig + 2 * (TC2_N / 32));                         // [TC2_STAGE_ROWS][128] staged scores ...
-    uint32_t* stg_id = reinterpret_cast<uint32_t*>(stg_sc + TC2_STAGE_ROWS * TC2_M);           // ... and ids of the epilogue rows
+    uint32_t* stg_id = reinterpret_cast<uint32_t*>(stg_sc + TC2_STAGE_ROWS * TC2_M * TC2_LISTS);   // ... and ids of the epilogue threads
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = V.ld / TC2_KB;
     const Tc2Sched sch(a);
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);   // one arrive per epilogue warp
+        mbar_init(&tmem_empty[0], TC2_EPI_WARPS); mbar_init(&tmem_empty[1], TC2_EPI_WARPS);   // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -170,8 +173,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread = query row =====
-        const int row = (warp & 3) * 32 + lane;
-        const int et = threadIdx.x - 128;   // 0..127
+        const int row = (warp & 3) * 32 + lane;                 // TMEM lane = query row of the block
+        const int half = (warp - 4) >> 2;                       // which TC2_N / TC2_LISTS columns of every tile this warp reads
+        const int et = threadIdx.x - 128;                       // 0 .. 32 * TC2_EPI_WARPS - 1
+        const int srow = half * TC2_M + row;                    // this thread's column of the staging area
         uint32_t tcount = 0;
         for (int qb = sch.g0; qb < a.n_qblocks; qb += sch.gstride) {
             int q = qb * TC2_M + row;
@@ -191,9 +196,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
             // the up-to-date threshold at merge time, so the list ends up exactly as if every column had been merged at once.
             auto merge_staged = [&]() {
                 for (int t = 0; t < n_st; ++t) {
-                    const float sc = stg_sc[t * TC2_M + row];
+                    const float sc = stg_sc[t * (TC2_M * TC2_LISTS) + srow];
                     if (sc > thr) {
-                        const uint32_t id = stg_id[t * TC2_M + row];
+                        const uint32_t id = stg_id[t * (TC2_M * TC2_LISTS) + srow];
                         const int pos = cnt < TC2_L ? cnt : minpos;
 #pragma unroll
                         for (int i = 0; i < TC2_L; ++i) if (i == pos) { ls[i] = sc; li[i] = id; }   // static indices: predicated moves
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
                     if ((uint32_t)v0 >= V.n) break;
                     uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
                     // per-tile column data: 1 / |v| (cosine) and the eligibility bits, by the 128 epilogue threads
-                    for (int j = et; j < TC2_N; j += 128) {
+                    for (int j = et; j < TC2_N; j += 32 * TC2_EPI_WARPS) {
                         uint32_t v = (uint32_t)v0 + j;
                         float ivn = 1.0f;
                         if (V.sim == SIM_COSINE) { float vn = v < V.n ? __ldg(V.norms + v) : 0.0f; ivn = vn > 0.0f ? __frcp_rn(vn) : 0.0f; }
@@ -228,10 +233,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
                         if (vb + 32 > V.n) w &= vb < V.n ? (0xFFFFFFFFu >> (32 - (V.n - vb))) : 0u;   // columns beyond the segment
                         elig[acc * (TC2_N / 32) + et] = w;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" :: "n"(32 * TC2_EPI_WARPS) : "memory");
                     mbar_wait(&tmem_full[acc], aph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int c0 = 0; c0 < TC2_N; c0 += 32) {
+                    for (int c0 = half * (TC2_N / TC2_LISTS); c0 < (half + 1) * (TC2_N / TC2_LISTS); c0 += 32) {
                         uint32_t r[32];
                         uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + acc * TC2_N + c0;
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -249,11 +254,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
                             if (V.sim == SIM_COSINE) sc = sc * inv_qn * inv_vn[acc * TC2_N + c0 + j];
                             const bool pass = ((ew >> j) & 1u) && sc > thr;
                             if (pass) {                                   // predicated stores: the row's staging area, in column order
-                                stg_sc[n_st * TC2_M + row] = sc;
-                                stg_id[n_st * TC2_M + row] = (uint32_t)v0 + c0 + j;
+                                stg_sc[n_st * (TC2_M * TC2_LISTS) + srow] = sc;
+                                stg_id[n_st * (TC2_M * TC2_LISTS) + srow] = (uint32_t)v0 + c0 + j;
                                 ++n_st;
                             }
-                            if ((j & 7) == 7 && __any_sync(0xFFFFFFFFu, n_st > TC2_STAGE_ROWS - 8)) merge_staged();
+                            if ((j & 3) == 3 && __any_sync(0xFFFFFFFFu, n_st > TC2_STAGE_ROWS - 4)) merge_staged();
                         }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -263,8 +268,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) scan_tc_filter_kernel(const __
                 }
             merge_staged();
             if (q < a.nq) {
-                float* os = a.cand_score + ((size_t)q * a.slots + sch.slot) * TC2_L;
-                uint32_t* oi = a.cand_id + ((size_t)q * a.slots + sch.slot) * TC2_L;
+                float* os = a.cand_score + (((size_t)q * a.slots + sch.slot) * TC2_LISTS + half) * TC2_L;
+                uint32_t* oi = a.cand_id + (((size_t)q * a.slots + sch.slot) * TC2_LISTS + half) * TC2_L;
 #pragma unroll
                 for (int i = 0; i < TC2_L; ++i) { os[i] = ls[i]; oi[i] = li[i]; }
             }
