@@ -69,3 +69,32 @@ def test_cost_model_is_a_host_function_equal_to_the_oracle():
                 for rq in (False, True):
                     for m in (16, 30):
                         assert call(total, matching, k, rq, m) == O.use_hnsw(total, matching, k, has_rabitq=rq, M=m), (total, matching, k, rq, m)
+
+
+def test_ctypes_structures_have_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/nidx_b200.h, as gcc lays it out, against the ctypes mirrors in nucliadb_b200/_lib.py
+    (a drift here corrupts arguments silently)."""
+    import ctypes as C
+    import subprocess
+
+    from nucliadb_b200 import _lib as L
+
+    pairs = [("nidx_vec_config", L.VecConfig), ("nidx_vec_search_params", L.VecSearchParams), ("nidx_txt_search_params", L.TxtSearchParams),
+             ("nidx_filter_node", L.FilterNode), ("nidx_rrf_source", L.RrfSource), ("nidx_shard_search_request", L.ShardSearchRequest),
+             ("nidx_shard_search_response", L.ShardSearchResponse)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "nidx_b200.h")}"', "int main(void) {"]
+    for cname, ct in pairs:
+        lines.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('printf("\\n");')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for (cname, ct), line in zip(pairs, out):
+        got = [int(x) for x in line.split()[1:]]
+        want = [C.sizeof(ct)] + [getattr(ct, f).offset for f, _ in ct._fields_]
+        assert got == want, (cname, got, want)
