@@ -134,8 +134,8 @@ class NidxBinding:
         return P.ShardCreated(id=self.new_shard(request.kbid, cfgs))
 
     # ---- index (lib.rs:83-111 -> process_index_message) ---------------------------------------------------------------------
-    def index(self, data: bytes) -> int:
-        msg = P.IndexMessage.FromString(bytes(data))
+    def index(self, bytes: bytes) -> int:  # noqa: A002  (the reference names the parameter `bytes`: nidx_binding.pyi:45, callers may pass it by keyword)
+        msg = P.IndexMessage.FromString(memoryview(bytes).tobytes())
         with self._lock:
             seq = self._seq
             self._seq += 1                                          # lib.rs:104-105: always incremented, even on failure

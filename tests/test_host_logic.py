@@ -213,3 +213,29 @@ def test_paragraph_store_round_trip_property():
         assert PS.decode_varint(enc, 0) == (u, len(enc)) and len(enc) in (1, 3, 5, 9)
 
     check()
+
+
+def test_nidx_binding_has_the_reference_surface():
+    """nidx/nidx_binding/nidx_binding.pyi:15-71 read here (the build container has the reference; elsewhere the test is skipped):
+    every method of the reference's NidxBinding exists with the same parameter names, and both port attributes are declared."""
+    import ast
+    import inspect
+
+    import pytest
+
+    pyi = "/root/reference/nidx/nidx_binding/nidx_binding.pyi"
+    if not os.path.exists(pyi):
+        pytest.skip("reference tree not present")
+    import nidx_binding
+
+    cls = next(n for n in ast.parse(open(pyi).read()).body if isinstance(n, ast.ClassDef) and n.name == "NidxBinding")
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef):
+            ours = getattr(nidx_binding.NidxBinding, node.name)
+            want = [a.arg for a in node.args.args]
+            got = list(inspect.signature(ours).parameters)
+            assert got == want, (node.name, got, want)
+        elif isinstance(node, ast.AnnAssign):
+            assert node.target.id in ("searcher_port", "api_port")
+    src = inspect.getsource(nidx_binding.NidxBinding.__init__)
+    assert "self.searcher_port" in src and "self.api_port" in src
